@@ -1,0 +1,130 @@
+/* mups.h -- C ABI of the B200-native MuPS (Multi-scale Point Statistics) hot path.
+ *
+ * Drop-in boundary for the one data-parallel path of sitzikbs/Nesti-Net this
+ * repository accelerates.  The reference has no FFI layer
+ * of its own (pure Python + TF1 graph), so each entry point cites the Python
+ * interface it replaces (paths relative to the reference root):
+ *
+ *   mups_index_*     <- utils/pcpnet_dataset.py:13-39   load_shape -> spatial.cKDTree(pts, 10)
+ *                       utils/pcpnet_dataset.py:281     bbdiag from pts.max(0) - pts.min(0)
+ *   mups_ball_query  <- utils/pcpnet_dataset.py:286-343 PointcloudPatchDataset.__getitem__
+ *                       (query_ball_point :304, subsample :320-321, centre :335-336, /rad :343)
+ *   mups_gmm_*       <- utils/utils.py:70-95 get_3d_grid_gmm as fed by
+ *                       train_n_est_w_experts.py:284-286 (w, mu, sqrt(cov) as float32)
+ *   mups_3dmfv       <- utils/tf_util.py:655-753 get_3dmfv_n_est (MUPS_FLAG_MASKED)
+ *                       utils/tf_util.py:578-652 get_3dmfv        (no MUPS_FLAG_MASKED)
+ *                       models/experts_n_est.py:59-76 MuPS assembly (MUPS_LAYOUT_MUPS)
+ *   mups_features    <- the two halves back to back (what one DataLoader item + one
+ *                       sess.run of the MuPS sub-graph compute, test_n_est_w_experts.py:129-148)
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; "dev" pointers are CUDA device pointers on the
+ *     device that is current when the call is made, "host" pointers are ordinary memory.
+ *   - every function returns MUPS_OK (0) or a negative mups_status; nothing throws or aborts
+ *     across the ABI.  mups_last_error() returns a thread-local description of the last failure.
+ *   - work is enqueued on the CUDA stream passed in (a cudaStream_t cast to void*; NULL = legacy
+ *     default stream).  No call synchronises unless its comment says so.
+ *   - an index / gmm handle is immutable after creation: concurrent queries from several host
+ *     threads or streams are legal.  One handle belongs to the device it was created on.
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails
+ *     with MUPS_ERR_CUDA.
+ */
+#ifndef MUPS_H_
+#define MUPS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUPS_ABI_VERSION 1
+
+typedef enum mups_status {
+    MUPS_OK = 0,
+    MUPS_ERR_INVALID = -1,   /* bad argument (the reference raises ValueError) */
+    MUPS_ERR_CUDA = -2,      /* CUDA runtime error, no device, launch failure  */
+    MUPS_ERR_NOMEM = -3,     /* allocation failed                              */
+    MUPS_ERR_UNSUPPORTED = -4/* shape outside the compiled limits              */
+} mups_status;
+
+/* flags of mups_3dmfv / mups_features */
+#define MUPS_FLAG_MASKED 1u        /* get_3dmfv_n_est semantics (n_eff mask, /n_eff); else get_3dmfv */
+#define MUPS_LAYOUT_MUPS 0u        /* out[b][g][s*20+c]  == [B,res,res,res,20*S] (experts_n_est.py:71-76) */
+#define MUPS_LAYOUT_CHANNEL 2u     /* out[b][s][c][g]    == per scale [B,20*G] flatten=True / [B,20,G] */
+#define MUPS_FLAG_NO_FASTPATH 4u   /* force the general (non-separable) statistics kernel */
+
+/* limits compiled into the kernels */
+#define MUPS_MAX_SCALES 8
+#define MUPS_MAX_POINTS_PER_PATCH 2048
+
+typedef struct mups_index mups_index;   /* uniform-grid spatial hash of one cloud (replaces cKDTree) */
+typedef struct mups_gmm mups_gmm;       /* device copy of (w, mu, sigma) + derived constants       */
+typedef void* mups_stream;              /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int mups_abi_version(void);
+const char* mups_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process (monotonic). */
+int64_t mups_launch_count(void);
+/* Process-wide tuning knobs.  "boundary_cap" (1..512, default 512): largest radix threshold group
+ * the subsample resolves without another refinement level (tests lower it to exercise the
+ * refinement path, which otherwise needs > ~500k neighbours in one ball).
+ * "stats_variant" (0 = automatic): force a statistics-kernel variant (benchmarking only). */
+int mups_set_option(const char* name, int64_t value);
+
+/* ---- spatial index (K1 bbox + K2 grid build) --------------------------------------------- */
+/* Builds the index of xyz_dev [n,3] float32 (row-major, device).  cell_frac: cell edge as a
+ * fraction of the bounding-box diagonal -- pass the largest patch radius that will be queried
+ * (<= 0 selects 0.07); any radius is still answered correctly, larger ones scan more cells.
+ * Asynchronous on `stream`; the handle may be used on the same stream immediately.
+ * The point data is copied: xyz_dev may be freed once the stream has passed the call. */
+int mups_index_create(mups_index** out, const float* xyz_dev, int64_t n, double cell_frac, mups_stream stream);
+/* Bounding box (float32 min/max per axis, what pts.min(0)/pts.max(0) return).  Synchronises the
+ * build stream on first use. */
+int mups_index_bbox(const mups_index* index, float min3_host[3], float max3_host[3]);
+int64_t mups_index_size(const mups_index* index);
+void mups_index_destroy(mups_index* index);
+
+/* ---- half 1: multi-radius ball query + seeded subsample + centre + normalise (K3 + K4) ---- */
+/* For each of the B centre points query_idx_dev[b] (indices into the indexed cloud) and each of
+ * the S radii r_abs_host[s] (absolute, float64, exactly the reference's bbdiag*patch_radius[s]):
+ *   nbr_total[b][s] = |{ j : sum_k (double(p_jk) - double(p_ck))^2 <= r*r }|  (cKDTree predicate)
+ *   n_eff[b][s]     = min(P, nbr_total)
+ *   the shared seeded selection (P smallest (philox key, index) pairs, ascending index order;
+ *   oracle/mups_oracle.py::select_subset) when nbr_total > P, else all neighbours ascending
+ *   nbr_idx[b][s][t]      = selected point index, -1 beyond n_eff           (may be NULL)
+ *   patches[b][s*P+t][k]  = (p_jk - p_ck) / float(r_s) in IEEE fp32, 0 beyond n_eff (may be NULL)
+ */
+int mups_ball_query(const mups_index* index, const int64_t* query_idx_dev, int64_t B,
+                    const double* r_abs_host, int S, int P, uint64_t seed,
+                    int32_t* nbr_idx_dev, int32_t* nbr_total_dev, float* patches_dev, int32_t* n_eff_dev,
+                    mups_stream stream);
+
+/* ---- GMM ----------------------------------------------------------------------------------- */
+/* w [G], mu [G,3], sigma [G,3] (std-dev) float32 on the HOST.  Detects the separable lattice
+ * (tensor-product means, one sigma per axis, uniform w) produced by get_3d_grid_gmm. */
+int mups_gmm_create(mups_gmm** out, const float* w_host, const float* mu_host, const float* sigma_host, int G);
+int mups_gmm_size(const mups_gmm* gmm);
+int mups_gmm_is_separable(const mups_gmm* gmm);
+void mups_gmm_destroy(mups_gmm* gmm);
+
+/* ---- half 2: 3DmFV statistics (K5) ---------------------------------------------------------- */
+/* patches_dev [B, S*P, 3] float32; n_eff_dev [B,S] int32 (required with MUPS_FLAG_MASKED, else
+ * ignored and may be NULL); out_dev: B*S*20*G float32 in the layout selected by `flags`. */
+int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_eff_dev,
+               int64_t B, int S, int P, uint32_t flags, float* out_dev, mups_stream stream);
+
+/* ---- both halves ---------------------------------------------------------------------------- */
+/* mups_ball_query followed by mups_3dmfv(MUPS_FLAG_MASKED) for the same B centres.
+ * patches_dev / n_eff_dev are caller-provided scratch of the sizes above (kept so that the
+ * caller can also read the patches); nbr_total_dev may be NULL. */
+int mups_features(const mups_index* index, const mups_gmm* gmm, const int64_t* query_idx_dev, int64_t B,
+                  const double* r_abs_host, int S, int P, uint64_t seed, uint32_t flags,
+                  float* patches_dev, int32_t* n_eff_dev, int32_t* nbr_total_dev, float* out_dev,
+                  mups_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUPS_H_ */

@@ -1,0 +1,407 @@
+// K3 (multi-radius ball query + seeded subsample) and K4 (gather, centre, normalise).
+// Replaces PointcloudPatchDataset.__getitem__ (reference utils/pcpnet_dataset.py:286-343):
+//   kdtree.query_ball_point (:304) -> uniform-grid scan with cKDTree's float64 predicate
+//   rng.choice (:320-321)          -> shared seeded selection: P smallest (philox key, index)
+//   gather / centre / /rad (:330-343) -> IEEE fp32 subtract and true division
+//
+// One CTA per centre point; all S radii are classified in the same scan of the candidate cells.
+// Pass A counts neighbours per radius and histograms the selection keys' top bits, the radix
+// threshold of every over-full radius is found in shared memory, pass B collects the selected
+// neighbours, which are then sorted by point index and written as normalised patches.
+#include "mups_common.cuh"
+
+namespace mups {
+
+constexpr int kQT = 256;            // threads per query CTA
+constexpr int kBinBits = 10;
+constexpr int kBins = 1 << kBinBits;
+constexpr int kBoundaryCap = 512;   // max entries of the threshold radix group resolved by rank counting
+
+struct QueryArgs {
+    const float4* sorted;
+    const uint32_t* cell_start;
+    const int32_t* pos_of;
+    const GridDesc* grid;
+    const int64_t* q;
+    int64_t n;
+    int S, P, Ppad;
+    int cap;                        // threshold groups up to this size are resolved by rank counting
+    double r2[MUPS_MAX_SCALES];     // r*r in float64 (cKDTree's upper bound for p=2)
+    float r2_lo[MUPS_MAX_SCALES];   // fp32 guard band around r2: below -> inside, above hi -> outside
+    float r2_hi[MUPS_MAX_SCALES];
+    float rf[MUPS_MAX_SCALES];      // float32(r): the divisor of pcpnet_dataset.py:343
+    float r_max;
+    float r2_hi_max;
+    uint32_t k0, k1;                // philox key = seed
+    int32_t* nbr_idx;
+    int32_t* nbr_total;
+    float* patches;
+    int32_t* n_eff;
+};
+
+struct QueryCtx {
+    float cx, cy, cz;
+    double cxd, cyd, czd;
+    int x0, x1, y0, y1, z0, z1;
+    float ox, oy, oz, cell;
+    uint32_t center;
+};
+
+// cKDTree leaf predicate: s = 0; s += d*d for x, y, z in float64 without FMA contraction; s <= r*r
+// (scipy/spatial/ckdtree/src/distance_base.h sqeuclidean_distance_double, m = 3).
+__device__ __forceinline__ bool inside_exact(const QueryCtx& c, const float4& p, double r2) {
+    const double dx = __dsub_rn((double)p.x, c.cxd), dy = __dsub_rn((double)p.y, c.cyd), dz = __dsub_rn((double)p.z, c.czd);
+    double s = __dmul_rn(dx, dx);
+    s = __dadd_rn(s, __dmul_rn(dy, dy));
+    s = __dadd_rn(s, __dmul_rn(dz, dz));
+    return s <= r2;
+}
+
+// Visits every neighbour of the centre (any radius): f(position in sorted, original index, bitmask of radii).
+template <class F>
+__device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx& c, F&& f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = kQT >> 5;
+    const int nx = c.x1 - c.x0 + 1, ny = c.y1 - c.y0 + 1, nz = c.z1 - c.z0 + 1;
+    const int ncell = nx * ny * nz;
+    const float slack = 1e-3f * c.cell;
+    for (int ci = warp; ci < ncell; ci += nwarp) {
+        const int ix = c.x0 + ci % nx, iy = c.y0 + (ci / nx) % ny, iz = c.z0 + ci / (nx * ny);
+        // distance from the centre to the cell's box (shrunk by the rounding slack of the cell assignment)
+        const float lx = c.ox + ix * c.cell, ly = c.oy + iy * c.cell, lz = c.oz + iz * c.cell;
+        const float gx = fmaxf(0.f, fmaxf(lx - c.cx, c.cx - (lx + c.cell)) - slack);
+        const float gy = fmaxf(0.f, fmaxf(ly - c.cy, c.cy - (ly + c.cell)) - slack);
+        const float gz = fmaxf(0.f, fmaxf(lz - c.cz, c.cz - (lz + c.cell)) - slack);
+        if (gx * gx + gy * gy + gz * gz > a.r2_hi_max) continue;
+        const uint32_t code = morton3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+        const uint32_t st = __ldg(a.cell_start + code), en = __ldg(a.cell_start + code + 1);
+        for (uint32_t i = st + lane; i < en; i += 32) {
+            const float4 p = __ldg(a.sorted + i);
+            const float dx = p.x - c.cx, dy = p.y - c.cy, dz = p.z - c.cz;
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d2 > a.r2_hi_max) continue;
+            uint32_t in = 0;
+#pragma unroll
+            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+                if (s < a.S && d2 <= a.r2_hi[s]) {
+                    if (d2 < a.r2_lo[s] || inside_exact(c, p, a.r2[s])) in |= 1u << s;
+                }
+            }
+            if (in) f(i, (uint32_t)__float_as_int(p.w), in);
+        }
+    }
+}
+
+// key of neighbour `idx` for radius s: word s&3 of philox(counter = (idx, centre, s>>2, 0))
+__device__ __forceinline__ void selection_keys(const QueryArgs& a, uint32_t center, uint32_t idx, uint32_t need_mask,
+                                               uint32_t key[MUPS_MAX_SCALES]) {
+    if (need_mask & 0x0Fu) {
+        const uint4 w = philox4x32_10(idx, center, 0u, 0u, a.k0, a.k1);
+        key[0] = w.x; key[1] = w.y; key[2] = w.z; key[3] = w.w;
+    }
+    if (need_mask & 0xF0u) {
+        const uint4 w = philox4x32_10(idx, center, 1u, 0u, a.k0, a.k1);
+        key[4] = w.x; key[5] = w.y; key[6] = w.z; key[7] = w.w;
+    }
+}
+
+// One warp finds, in hist[0..nbins), the bin T holding the `need`-th smallest element.
+// Returns T, the population below T and the population of T (valid on all lanes).
+__device__ __forceinline__ void warp_find_threshold(const uint32_t* hist, int nbins, uint32_t need, int lane,
+                                                    uint32_t* T, uint32_t* below, uint32_t* group) {
+    const int per = (nbins + 31) / 32;
+    uint32_t mine = 0;
+    for (int k = 0; k < per; ++k) {
+        const int b = lane * per + k;
+        mine += b < nbins ? hist[b] : 0u;
+    }
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t exc = inc - mine;
+    const bool owner = exc < need && need <= inc;
+    uint32_t t_bin = 0, t_below = 0, t_group = 0;
+    if (owner) {
+        uint32_t run = exc;
+        for (int k = 0; k < per; ++k) {
+            const int b = lane * per + k;
+            const uint32_t h = b < nbins ? hist[b] : 0u;
+            if (run < need && need <= run + h) { t_bin = b; t_below = run; t_group = h; break; }
+            run += h;
+        }
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, owner);
+    const int src = ballot ? (__ffs(ballot) - 1) : 0;
+    *T = __shfl_sync(0xffffffffu, t_bin, src);
+    *below = __shfl_sync(0xffffffffu, t_below, src);
+    *group = __shfl_sync(0xffffffffu, t_group, src);
+}
+
+__global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);                                  // [S][kBins]
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(hist + a.S * kBins);     // [S][Ppad]  (idx << 32 | pos)
+    unsigned long long* bnd = sel + (size_t)a.S * a.Ppad;                                    // [S][kBoundaryCap] (key << 32 | hit slot)
+    uint32_t* bnd_pos = reinterpret_cast<uint32_t*>(bnd + (size_t)a.S * kBoundaryCap);       // [S][kBoundaryCap] position in sorted
+    __shared__ uint32_t s_cnt[MUPS_MAX_SCALES], s_nsel[MUPS_MAX_SCALES], s_nb[MUPS_MAX_SCALES];
+    __shared__ uint32_t s_prefix[MUPS_MAX_SCALES], s_bits[MUPS_MAX_SCALES], s_need[MUPS_MAX_SCALES];
+    __shared__ uint32_t s_unresolved;
+
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = a.S, P = a.P;
+    const int64_t q = a.q[b];
+
+    for (int i = tid; i < S * kBins; i += kQT) hist[i] = 0u;
+    if (tid < MUPS_MAX_SCALES) {
+        s_cnt[tid] = 0u; s_nsel[tid] = 0u; s_nb[tid] = 0u; s_prefix[tid] = 0u; s_bits[tid] = 0u; s_need[tid] = 0u;
+    }
+    if (tid == 0) s_unresolved = 0u;
+
+    if (q < 0 || q >= a.n) {   // invalid centre: empty patch, total = -1
+        for (int i = tid; i < S * P; i += kQT) {
+            if (a.patches) { float* o = a.patches + (b * S * P + i) * 3; o[0] = 0.f; o[1] = 0.f; o[2] = 0.f; }
+            if (a.nbr_idx) a.nbr_idx[b * S * P + i] = -1;
+        }
+        if (tid < S) { a.n_eff[b * S + tid] = 0; if (a.nbr_total) a.nbr_total[b * S + tid] = -1; }
+        return;
+    }
+
+    QueryCtx c;
+    {
+        const GridDesc g = *a.grid;
+        const float4 pc = __ldg(a.sorted + __ldg(a.pos_of + q));
+        c.cx = pc.x; c.cy = pc.y; c.cz = pc.z;
+        c.cxd = (double)pc.x; c.cyd = (double)pc.y; c.czd = (double)pc.z;
+        c.ox = g.origin[0]; c.oy = g.origin[1]; c.oz = g.origin[2]; c.cell = g.cell;
+        c.center = (uint32_t)q;
+        // |floor(u) - floor(v)| <= floor(|u - v|) + 1; 1e-4 covers the fp32 rounding of the cell assignment
+        const int R = (int)floorf(a.r_max * g.inv_cell + 1e-4f) + 1;
+        const int ix = cell_coord(pc.x, g.origin[0], g.inv_cell, g.dims[0]);
+        const int iy = cell_coord(pc.y, g.origin[1], g.inv_cell, g.dims[1]);
+        const int iz = cell_coord(pc.z, g.origin[2], g.inv_cell, g.dims[2]);
+        c.x0 = max(ix - R, 0); c.x1 = min(ix + R, g.dims[0] - 1);
+        c.y0 = max(iy - R, 0); c.y1 = min(iy + R, g.dims[1] - 1);
+        c.z0 = max(iz - R, 0); c.z1 = min(iz + R, g.dims[2] - 1);
+    }
+    __syncthreads();
+
+    // ---- pass A: neighbour count per radius + first-level key histogram -------------------------
+    {
+        uint32_t cnt[MUPS_MAX_SCALES];
+#pragma unroll
+        for (int s = 0; s < MUPS_MAX_SCALES; ++s) cnt[s] = 0u;
+        for_each_hit(a, c, [&](uint32_t, uint32_t idx, uint32_t in) {
+            uint32_t key[MUPS_MAX_SCALES];
+            selection_keys(a, c.center, idx, in, key);
+#pragma unroll
+            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+                if (in & (1u << s)) {
+                    ++cnt[s];
+                    atomicAdd(hist + s * kBins + (key[s] >> (32 - kBinBits)), 1u);
+                }
+            }
+        });
+#pragma unroll
+        for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+            if (s < S) {
+                uint32_t v = cnt[s];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && v) atomicAdd(s_cnt + s, v);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- radix threshold of the over-full radii (warp s handles radius s) -------------------------
+    if (warp < S && s_cnt[warp] > (uint32_t)P) {
+        uint32_t T, below, group;
+        warp_find_threshold(hist + warp * kBins, kBins, (uint32_t)P, lane, &T, &below, &group);
+        if (lane == 0) {
+            s_prefix[warp] = T; s_bits[warp] = kBinBits; s_need[warp] = (uint32_t)P - below;
+            if (group > (uint32_t)a.cap) atomicOr(&s_unresolved, 1u << warp);
+        }
+    }
+    __syncthreads();
+
+    // ---- refinement levels (only when a threshold group exceeds kBoundaryCap: > ~500k neighbours) ----
+    while (s_unresolved) {
+        const uint32_t unresolved = s_unresolved;
+        __syncthreads();
+        for (int i = tid; i < S * kBins; i += kQT)
+            if (unresolved & (1u << (i / kBins))) hist[i] = 0u;
+        if (tid == 0) s_unresolved = 0u;
+        __syncthreads();
+        for_each_hit(a, c, [&](uint32_t, uint32_t idx, uint32_t in) {
+            in &= unresolved;
+            if (!in) return;
+            uint32_t key[MUPS_MAX_SCALES];
+            selection_keys(a, c.center, idx, in, key);
+#pragma unroll
+            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+                if (in & (1u << s)) {
+                    const uint32_t bits = s_bits[s];
+                    const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
+                    if ((key[s] >> (32u - bits)) == s_prefix[s])
+                        atomicAdd(hist + s * kBins + ((key[s] >> (32u - bits - nb)) & ((1u << nb) - 1u)), 1u);
+                }
+            }
+        });
+        __syncthreads();
+        if (warp < S && (unresolved & (1u << warp))) {
+            const uint32_t bits = s_bits[warp];
+            const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
+            uint32_t T, below, group;
+            warp_find_threshold(hist + warp * kBins, 1 << nb, s_need[warp], lane, &T, &below, &group);
+            if (lane == 0) {
+                s_prefix[warp] = (s_prefix[warp] << nb) | T; s_bits[warp] = bits + nb; s_need[warp] -= below;
+                // with all 32 key bits fixed the group is a set of exact key ties; more than
+                // kBoundaryCap of them cannot be told apart here (never seen: needs >500 equal 32-bit keys)
+                if (group > (uint32_t)a.cap && bits + nb < 32u) atomicOr(&s_unresolved, 1u << warp);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- pass B: collect the selection -----------------------------------------------------------------
+    {
+        uint32_t over = 0;   // radii that need keys
+        for (int s = 0; s < S; ++s) over |= (s_cnt[s] > (uint32_t)P) ? (1u << s) : 0u;
+        for_each_hit(a, c, [&](uint32_t pos, uint32_t idx, uint32_t in) {
+            uint32_t key[MUPS_MAX_SCALES];
+            selection_keys(a, c.center, idx, in & over, key);
+#pragma unroll
+            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+                if (!(in & (1u << s))) continue;
+                bool take = true;
+                if (over & (1u << s)) {
+                    const uint32_t hp = key[s] >> (32u - s_bits[s]);
+                    take = hp < s_prefix[s];
+                    if (hp == s_prefix[s]) {
+                        const uint32_t slot = atomicAdd(s_nb + s, 1u);
+                        if (slot < (uint32_t)kBoundaryCap) {
+                            bnd[s * kBoundaryCap + slot] = ((unsigned long long)key[s] << 32) | idx;
+                            bnd_pos[s * kBoundaryCap + slot] = pos;
+                        }
+                    }
+                }
+                if (take) {
+                    const uint32_t slot = atomicAdd(s_nsel + s, 1u);
+                    if (slot < (uint32_t)a.Ppad) sel[(size_t)s * a.Ppad + slot] = ((unsigned long long)idx << 32) | pos;
+                }
+            }
+        });
+    }
+    __syncthreads();
+
+    // ---- threshold group: keep the `need` smallest (key, index) pairs ------------------------------------
+    for (int s = 0; s < S; ++s) {
+        const uint32_t m = min(s_nb[s], (uint32_t)kBoundaryCap);
+        const uint32_t need = s_need[s];
+        for (uint32_t i = tid; i < m; i += kQT) {
+            const unsigned long long mine = bnd[s * kBoundaryCap + i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < m; ++j) rank += bnd[s * kBoundaryCap + j] < mine ? 1u : 0u;
+            if (rank < need) {
+                const uint32_t slot = atomicAdd(s_nsel + s, 1u);
+                if (slot < (uint32_t)a.Ppad)
+                    sel[(size_t)s * a.Ppad + slot] = ((mine & 0xFFFFFFFFull) << 32) | bnd_pos[s * kBoundaryCap + i];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- sort each radius' selection by point index (bitonic, shared memory), then K4 ----------------------
+    for (int s = 0; s < S; ++s) {
+        const uint32_t total = s_cnt[s];
+        const uint32_t ne = min(total, (uint32_t)P);
+        unsigned long long* v = sel + (size_t)s * a.Ppad;
+        uint32_t np2 = 1;
+        while (np2 < ne) np2 <<= 1;
+        for (uint32_t i = ne + tid; i < np2; i += kQT) v[i] = ~0ull;
+        __syncthreads();
+        for (uint32_t k = 2; k <= np2; k <<= 1) {
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = tid; i < np2; i += kQT) {
+                    const uint32_t l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long x = v[i], y = v[l];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { v[i] = y; v[l] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // K4: gather, centre on the query point, divide by float32(r)  (pcpnet_dataset.py:330-343)
+        const float rf = a.rf[s];
+        for (uint32_t t = tid; t < (uint32_t)P; t += kQT) {
+            float ox = 0.f, oy = 0.f, oz = 0.f;
+            int32_t id = -1;
+            if (t < ne) {
+                const unsigned long long e = v[t];
+                id = (int32_t)(e >> 32);
+                const float4 p = __ldg(a.sorted + (uint32_t)(e & 0xFFFFFFFFull));
+                ox = __fdiv_rn(__fsub_rn(p.x, c.cx), rf);
+                oy = __fdiv_rn(__fsub_rn(p.y, c.cy), rf);
+                oz = __fdiv_rn(__fsub_rn(p.z, c.cz), rf);
+            }
+            if (a.patches) {
+                float* o = a.patches + ((b * S + s) * (int64_t)P + t) * 3;
+                o[0] = ox; o[1] = oy; o[2] = oz;
+            }
+            if (a.nbr_idx) a.nbr_idx[(b * S + s) * (int64_t)P + t] = id;
+        }
+        if (tid == 0) {
+            a.n_eff[b * S + s] = (int32_t)ne;
+            if (a.nbr_total) a.nbr_total[b * S + s] = (int32_t)total;
+        }
+    }
+}
+
+int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const double* r_abs, int S, int P,
+                      uint64_t seed, int32_t* nbr_idx, int32_t* nbr_total, float* patches, int32_t* n_eff,
+                      cudaStream_t st) {
+    QueryArgs a;
+    a.sorted = ix->sorted; a.cell_start = ix->cell_start; a.pos_of = ix->pos_of; a.grid = ix->grid;
+    a.q = q; a.n = ix->n; a.S = S; a.P = P;
+    int ppad = 1;
+    while (ppad < P) ppad <<= 1;
+    a.Ppad = ppad;
+    a.cap = g_boundary_cap.load();
+    double rmax = 0.0;
+    float hi_max = 0.f;
+    for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+        const double r = s < S ? r_abs[s] : 0.0;
+        a.r2[s] = r * r;
+        a.r2_lo[s] = (float)(a.r2[s] * (1.0 - 4e-6));
+        a.r2_hi[s] = (float)(a.r2[s] * (1.0 + 4e-6));
+        a.rf[s] = (float)r;
+        if (r > rmax) rmax = r;
+        if (a.r2_hi[s] > hi_max) hi_max = a.r2_hi[s];
+    }
+    a.r_max = (float)(rmax * (1.0 + 1e-6));
+    a.r2_hi_max = hi_max;
+    a.k0 = (uint32_t)(seed & 0xFFFFFFFFull); a.k1 = (uint32_t)(seed >> 32);
+    a.nbr_idx = nbr_idx; a.nbr_total = nbr_total; a.patches = patches; a.n_eff = n_eff;
+    const size_t smem = (size_t)S * kBins * 4 + (size_t)S * ppad * 8 + (size_t)S * kBoundaryCap * 12;
+    if (smem > 200 * 1024) {
+        set_error("ball query: S=%d, P=%d needs %zu bytes of shared memory", S, P, smem);
+        return MUPS_ERR_UNSUPPORTED;
+    }
+    static std::atomic<size_t> configured{0};
+    if (smem > 48 * 1024 && configured.load() < smem) {
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured.store(200 * 1024);
+    }
+    if (B > 0) {
+        ball_query_kernel<<<(unsigned)B, kQT, smem, st>>>(a);
+        MUPS_CHECK_LAUNCH();
+    }
+    return MUPS_OK;
+}
+
+}  // namespace mups

@@ -1,0 +1,68 @@
+"""Multi-GPU partitioning of the MuPS path.
+
+The reference is single-process; the path shards naturally: every query point is independent
+given the read-only cloud.  One process per GPU (torch.distributed, NCCL on GPUs / gloo in the
+CPU tests), the cloud and GMM are replicated on every rank (each rank builds its own index: the
+build is far cheaper than shipping it), the query list is split into contiguous ranges and each
+rank writes its own feature slab.  There is NO collective on the data path; ``gather_slabs`` is
+the optional final all-gather for a single-rank consumer.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, world_size, weights=None):
+    """Contiguous split of ``n_items`` into ``world_size`` ranges -> int64 [world_size + 1].
+
+    Without weights the ranges differ by at most one item.  With per-item ``weights`` (estimated
+    work, e.g. the neighbour count at the largest radius of a cheap count pass) the cut points
+    balance the prefix sum of the weights -- needed for clouds of non-uniform density."""
+    n_items, world_size = int(n_items), int(world_size)
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    if weights is None:
+        base, extra = divmod(n_items, world_size)
+        sizes = np.full(world_size, base, dtype=np.int64)
+        sizes[:extra] += 1
+        return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    w = np.asarray(weights, dtype=np.float64).reshape(-1)
+    if len(w) != n_items:
+        raise ValueError("weights must have one entry per item")
+    if np.any(w < 0):
+        raise ValueError("weights must be non-negative")
+    csum = np.cumsum(w)
+    total = csum[-1] if n_items else 0.0
+    if total <= 0:
+        return shard_bounds(n_items, world_size)
+    targets = total * np.arange(1, world_size, dtype=np.float64) / world_size
+    cuts = np.searchsorted(csum, targets, side="left") + 1
+    bounds = np.concatenate([[0], np.minimum(cuts, n_items), [n_items]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+def shard_queries(query_idx, rank, world_size, weights=None):
+    """This rank's contiguous slice of the query list and its (start, end) in the full list."""
+    b = shard_bounds(len(query_idx), world_size, weights)
+    return query_idx[b[rank]:b[rank + 1]], int(b[rank]), int(b[rank + 1])
+
+
+def gather_slabs(slab, group=None):
+    """All-gather per-rank feature slabs [B_r, ...] of unequal B_r along dim 0 (the only
+    collective of the path; only for a single-rank consumer).  Works with NCCL (CUDA slabs) and
+    gloo (CPU slabs)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return slab
+    world = dist.get_world_size(group)
+    count = torch.tensor([slab.shape[0]], dtype=torch.int64, device=slab.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    bmax = max(counts)
+    padded = slab
+    if slab.shape[0] < bmax:
+        pad = torch.zeros((bmax - slab.shape[0],) + tuple(slab.shape[1:]), dtype=slab.dtype, device=slab.device)
+        padded = torch.cat([slab, pad], dim=0)
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)

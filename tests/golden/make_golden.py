@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/.
+
+Run in the BUILD container only (it imports the unmodified reference from
+/root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+half1_reference.npz  -- outputs of the reference's own
+    utils/pcpnet_dataset.py::PointcloudPatchDataset.__getitem__ (unmodified,
+    imported from /root/reference/utils) on a small synthetic cloud:
+    raw cKDTree neighbour lists, effective point counts, absolute radii and
+    the patch tensors.  Rows of patches whose neighbourhood was not subsampled
+    are stored re-ordered to ascending neighbour index (the kd-tree returns
+    traversal order); subsampled patches are stored as the reference produced
+    them (only the subset property can be checked for those, the reference's
+    draw comes from a stateful stream shared by all patches).
+half2_oracle.npz -- inputs/outputs of the recorded fp32 transliteration of
+    utils/tf_util.py:655-753 / :578-652 (TensorFlow 1.12 is not installable:
+    PARITY UNPINNED), written only after the independent float64 restatement
+    agrees within 1e-6.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+from oracle import mups_oracle as orc  # noqa: E402
+
+REF_UTILS = "/root/reference/utils"
+
+
+def make_half1():
+    sys.path.insert(0, REF_UTILS)
+    import pcpnet_dataset as ref  # the unmodified reference module
+
+    cases = {}
+    # case A: small patches so both branches (len<=P and len>P) occur
+    # case B: the reference's P=512 with 4 scales
+    specs = {
+        "A": dict(n=4000, cloud_id=0, P=48, radii=[0.03, 0.08, 0.15], nq=96, noise=0.0),
+        "B": dict(n=30000, cloud_id=1, P=512, radii=[0.01, 0.03, 0.05, 0.07], nq=32, noise=0.002),
+    }
+    for name, sp in specs.items():
+        pts = orc.synthetic_cloud(sp["n"], cloud_id=sp["cloud_id"], noise=sp["noise"])
+        # duplicate a few points and put a query on the bbox corner (edge cases)
+        pts[10] = pts[11]
+        pts[12] = pts[11]
+        with tempfile.TemporaryDirectory() as d:
+            # np.loadtxt(...).astype('float32') must give back the same float32 bits: %.9g round-trips
+            np.savetxt(os.path.join(d, "cloud.xyz"), pts, fmt="%.9g")
+            with open(os.path.join(d, "list.txt"), "w") as f:
+                f.write("cloud\n")
+            ds = ref.PointcloudPatchDataset(
+                root=d, shape_list_filename="list.txt", patch_radius=sp["radii"],
+                points_per_patch=sp["P"], patch_features=[], seed=3627473, identical_epochs=False,
+                use_pca=False, center="point", point_tuple=1, cache_capacity=100,
+                point_count_std=0, sparse_patches=False)
+            shape = ds.shape_cache.get(0)
+            assert np.array_equal(shape.pts, pts), "xyz text round trip changed the float32 bits"
+            rng = np.random.RandomState(7)
+            q = np.unique(np.concatenate([
+                rng.choice(sp["n"], sp["nq"] - 6, replace=False),
+                [10, 11, 12, int(pts[:, 0].argmax()), int(pts[:, 1].argmin()), int(pts[:, 2].argmax())]]))
+            S, P = len(sp["radii"]), sp["P"]
+            rads = ds.patch_radius_absolute[0]
+            patches = np.zeros((len(q), S * P, 3), np.float32)
+            n_eff = np.zeros((len(q), S), np.int32)
+            nbr_flat, nbr_off, subsampled = [], [0], np.zeros((len(q), S), bool)
+            for b, c in enumerate(q):
+                item = ds[int(c)]
+                pp = item[0].numpy().copy()
+                ne = np.asarray(item[-1]).astype(np.int32)
+                n_eff[b] = ne
+                for s, rad in enumerate(rads):
+                    raw = np.array(shape.kdtree.query_ball_point(shape.pts[int(c), :], rad))
+                    nbr_flat.append(np.sort(raw))
+                    nbr_off.append(nbr_off[-1] + len(raw))
+                    if len(raw) <= P:
+                        order = np.argsort(raw, kind="stable")
+                        pp[s * P: s * P + len(raw)] = pp[s * P: s * P + len(raw)][order]
+                    else:
+                        subsampled[b, s] = True
+                patches[b] = pp
+            cases[name] = dict(
+                pts=pts, query_idx=q.astype(np.int64), patch_radius=np.asarray(sp["radii"], np.float64),
+                P=np.int64(P), radii_abs=np.asarray(rads, np.float64),
+                bbdiag=np.float64(rads[0] / sp["radii"][0]),
+                nbr_flat=np.concatenate(nbr_flat).astype(np.int32), nbr_off=np.asarray(nbr_off, np.int64),
+                n_eff=n_eff, patches=patches, subsampled=subsampled)
+            print("half1 case", name, "queries", len(q), "subsampled", int(subsampled.sum()),
+                  "of", subsampled.size, "max len", int(np.diff(nbr_off).max()))
+    flat = {}
+    for name, c in cases.items():
+        for k, v in c.items():
+            flat["%s_%s" % (name, k)] = v
+    np.savez_compressed(os.path.join(HERE, "half1_reference.npz"), **flat)
+
+
+def make_half2():
+    rng = np.random.RandomState(11)
+    out = {}
+    # (res, P, variance, n_eff list)
+    specs = {
+        "g3": (3, 16, 0.11, [1, 2, 5, 14, 15, 16]),
+        "g8": (8, 64, 0.0156, [1, 2, 30, 62, 63, 64]),
+        "g8p512": (8, 512, 0.0156, [17, 510, 511, 512]),
+    }
+    for name, (res, P, var, neffs) in specs.items():
+        w, mu, sigma = orc.gmm_feed(*orc.get_3d_grid_gmm([res] * 3, var))
+        B = len(neffs)
+        pts = np.zeros((B, P, 3), np.float32)
+        for b, ne in enumerate(neffs):
+            x = rng.normal(size=(ne, 3)) * 0.4
+            x /= np.maximum(1.0, np.linalg.norm(x, axis=1, keepdims=True))   # inside the unit ball
+            x[0] = 0.0                                                     # the centre is its own neighbour
+            pts[b, :ne] = x
+        ne = np.asarray(neffs, np.int32)
+        fv = orc.get_3dmfv_n_est(pts, w, mu, sigma, flatten=False, n_original_points=ne)
+        f64 = orc.get_3dmfv_n_est_f64(pts, w, mu, sigma, ne, masked=True)
+        err = np.abs(fv - f64).max()
+        assert err < 1e-6, (name, err)
+        fv_plain = orc.get_3dmfv(pts, w, mu, sigma, flatten=False)
+        f64_plain = orc.get_3dmfv_n_est_f64(pts, w, mu, sigma, None, masked=False)
+        err2 = np.abs(fv_plain - f64_plain).max()
+        assert err2 < 1e-6, (name, err2)
+        print("half2 case", name, "fp32 vs f64 max abs err", err, err2)
+        out[name + "_points"] = pts
+        out[name + "_n_eff"] = ne
+        out[name + "_w"] = w
+        out[name + "_mu"] = mu
+        out[name + "_sigma"] = sigma
+        out[name + "_fv_n_est"] = fv
+        out[name + "_fv_plain"] = fv_plain
+    # general (non-grid) GMM: non-uniform w, anisotropic per-Gaussian sigma
+    G, P = 27, 32
+    w = rng.uniform(0.5, 1.5, G); w = (w / w.sum()).astype(np.float32)
+    mu = rng.uniform(-0.8, 0.8, (G, 3)).astype(np.float32)
+    sigma = rng.uniform(0.2, 0.5, (G, 3)).astype(np.float32)
+    neffs = np.asarray([1, 7, 30, 31, 32], np.int32)
+    pts = np.zeros((len(neffs), P, 3), np.float32)
+    for b, ne in enumerate(neffs):
+        x = rng.uniform(-0.7, 0.7, (ne, 3)); x[0] = 0
+        pts[b, :ne] = x
+    fv = orc.get_3dmfv_n_est(pts, w, mu, sigma, flatten=False, n_original_points=neffs)
+    f64 = orc.get_3dmfv_n_est_f64(pts, w, mu, sigma, neffs, masked=True)
+    assert np.abs(fv - f64).max() < 1e-6
+    fv_plain = orc.get_3dmfv(pts, w, mu, sigma, flatten=False)
+    f64_plain = orc.get_3dmfv_n_est_f64(pts, w, mu, sigma, None, masked=False)
+    assert np.abs(fv_plain - f64_plain).max() < 1e-6
+    print("half2 case general, fp32 vs f64", np.abs(fv - f64).max(), np.abs(fv_plain - f64_plain).max())
+    out.update(gen_points=pts, gen_n_eff=neffs, gen_w=w, gen_mu=mu, gen_sigma=sigma,
+               gen_fv_n_est=fv, gen_fv_plain=fv_plain)
+    np.savez_compressed(os.path.join(HERE, "half2_oracle.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_half1()
+    make_half2()

@@ -1,0 +1,169 @@
+"""CPU tests of the host logic: the C-ABI library loads and exports every symbol include/mups.h
+declares, argument validation and error strings (no compute without a GPU), the grid GMM
+mirror, query sharding, the world_size-2 gloo path of the slab gather, and that the product
+never reaches into oracle/."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import nesti_net_b200 as mb
+from nesti_net_b200 import _lib
+from oracle import mups_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mups.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(mups_[a-z0-9_]+)\s*\(", body)))
+    assert declared, "no declarations parsed"
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), "libmups_b200.so does not export %s" % name
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.mups_abi_version() == 1
+
+
+def test_argument_validation_without_compute():
+    L = _lib.load()
+    h = ctypes.c_void_p()
+    fp = ctypes.POINTER(ctypes.c_float)
+    w = np.full(8, 1 / 8, np.float32)
+    mu = np.zeros((8, 3), np.float32)
+    sg = np.ones((8, 3), np.float32)
+    args = lambda a: a.ctypes.data_as(fp)
+    assert L.mups_gmm_create(ctypes.byref(h), args(w), args(mu), args(sg), 0) == _lib.MUPS_ERR_INVALID
+    assert b"out of range" in L.mups_last_error()
+    bad = sg.copy(); bad[3, 1] = 0
+    assert L.mups_gmm_create(ctypes.byref(h), args(w), args(mu), args(bad), 8) == _lib.MUPS_ERR_INVALID
+    assert b"sigma[3][1]" in L.mups_last_error()
+    assert L.mups_3dmfv(None, None, None, 1, 1, 16, 1, None, None) == _lib.MUPS_ERR_INVALID
+    assert L.mups_ball_query(None, None, 1, None, 1, 16, 0, None, None, None, None, None) == _lib.MUPS_ERR_INVALID
+    assert L.mups_index_create(ctypes.byref(h), None, 10, 0.07, None) == _lib.MUPS_ERR_INVALID
+    assert L.mups_set_option(b"no_such_option", 1) == _lib.MUPS_ERR_INVALID
+    assert L.mups_set_option(b"boundary_cap", 0) == _lib.MUPS_ERR_INVALID
+    assert L.mups_set_option(b"boundary_cap", 512) == _lib.MUPS_OK
+    with pytest.raises(ValueError):
+        _lib.check(L.mups_set_option(b"boundary_cap", 100000))
+    if not torch.cuda.is_available():
+        # no CPU fallback: a valid request fails loudly with MUPS_ERR_CUDA
+        assert L.mups_gmm_create(ctypes.byref(h), args(w), args(mu), args(sg), 8) == _lib.MUPS_ERR_CUDA
+        assert b"CUDA" in L.mups_last_error() or b"device" in L.mups_last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_python_api_fails_loudly_without_gpu():
+    w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([3] * 3, 0.1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mb.tf_util.get_3dmfv_n_est(np.zeros((1, 8, 3), np.float32), w, mu, sg, n_original_points=[4])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mb.PointIndex(np.zeros((10, 3), np.float32))
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "nesti-net_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "libmups_oracle" not in text and "c_oracle" not in text, f
+
+
+def test_grid_gmm_mirror_is_bit_identical():
+    for n, var in [(3, 0.11), (5, 0.04), (8, 0.0156), (16, 0.00390625)]:
+        g = mb.get_3d_grid_gmm([n] * 3, var)
+        w, mu, cov = orc.get_3d_grid_gmm([n] * 3, var)
+        assert np.array_equal(g.weights_, w) and np.array_equal(g.means_, mu) and np.array_equal(g.covariances_, cov)
+    g = mb.get_3d_grid_gmm([2, 3, 4], 0.1)
+    w, mu, cov = orc.get_3d_grid_gmm([2, 3, 4], 0.1)
+    assert np.array_equal(g.means_, mu)
+
+
+def test_shard_bounds():
+    sb = mb.dist.shard_bounds
+    assert list(sb(10, 3)) == [0, 4, 7, 10]
+    assert list(sb(0, 4)) == [0, 0, 0, 0, 0]
+    assert list(sb(3, 8)) == [0, 1, 2, 3, 3, 3, 3, 3, 3]
+    rng = np.random.RandomState(0)
+    for world in (1, 2, 4, 8):
+        w = rng.gamma(0.5, 1.0, 100000)            # heavy-tailed work estimate
+        b = sb(len(w), world, w)
+        assert b[0] == 0 and b[-1] == len(w) and np.all(np.diff(b) >= 0)
+        loads = np.add.reduceat(w, b[:-1])[: world]
+        assert loads.max() <= w.sum() / world + w.max() + 1e-9
+    q = np.arange(101)
+    parts = [mb.dist.shard_queries(q, r, 4)[0] for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), q)
+    with pytest.raises(ValueError):
+        sb(5, 2, [1, 2, 3])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n_queries, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q = np.arange(n_queries, dtype=np.int64) * 3
+        weights = (np.arange(n_queries) % 7 + 1).astype(np.float64)       # unequal shards
+        mine, lo, hi = mb.dist.shard_queries(q, rank, world, weights)
+        # a stand-in slab (the product computes slabs on the GPU; here only the plumbing is under test)
+        slab = torch.from_numpy(np.stack([mine.astype(np.float32), mine.astype(np.float32) ** 2], 1)).reshape(len(mine), 2)
+        full = mb.dist.gather_slabs(slab)
+        expect = torch.from_numpy(np.stack([q.astype(np.float32), q.astype(np.float32) ** 2], 1))
+        ret[rank] = bool(torch.equal(full, expect)) and (hi - lo) == len(mine)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_slab_gather():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gloo_worker, args=(world, _free_port(), 1001, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_samplers():
+    class DS(object):
+        shape_names = ["a", "b", "c"]
+        shape_patch_count = [10, 5, 20]
+    ds = DS()
+    seq = mb.pcpnet_dataset.SequentialPointcloudPatchSampler(ds)
+    assert list(seq) == list(range(35)) and len(seq) == 35
+    rnd = mb.pcpnet_dataset.RandomPointcloudPatchSampler(ds, patches_per_shape=8, seed=1, identical_epochs=True)
+    a, b = list(rnd), list(rnd)
+    assert len(a) == len(rnd) == 8 + 5 + 8 and len(set(a)) == len(a) and a == b and max(a) < 35
+    ssr = mb.pcpnet_dataset.SequentialShapeRandomPointcloudPatchSampler(ds, 8, seed=1, sequential_shapes=True)
+    idx = list(ssr)
+    assert len(idx) == 21 and all(i < 10 for i in idx[:8]) and all(10 <= i < 15 for i in idx[8:13]) and all(i >= 15 for i in idx[13:])
+
+
+def test_dataset_rejects_options_off_the_hot_path(tmp_path):
+    (tmp_path / "list.txt").write_text("cloud\n")
+    kw = dict(root=str(tmp_path), shape_list_filename="list.txt", patch_radius=[0.05], points_per_patch=16,
+              patch_features=[], seed=1)
+    with pytest.raises(NotImplementedError):
+        mb.pcpnet_dataset.PointcloudPatchDataset(use_pca=True, **kw)
+    with pytest.raises(ValueError):
+        mb.pcpnet_dataset.PointcloudPatchDataset(use_pca=False, center="bogus", **kw)
+    with pytest.raises(ValueError):
+        mb.pcpnet_dataset.PointcloudPatchDataset(use_pca=False, **dict(kw, patch_features=["bogus"]))
+    with pytest.raises(ValueError):
+        mb.provider.get_data_loader(outputs=["bogus"], indir=str(tmp_path), dataset_name="list.txt")

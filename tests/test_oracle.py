@@ -1,0 +1,169 @@
+"""CPU tests: the oracle against the golden fixtures (outputs of the unmodified reference for
+half 1, recorded transliteration + float64 cross-check for half 2) and against itself (numpy
+restatement vs C port vs float64)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import mups_oracle as orc
+
+TOL_ABS, TOL_REL = 1e-6, 1e-5          # BASELINE.json north_star: 1e-5 relative, 1e-6 absolute in fp32
+
+
+def frac_outside(got, ref):
+    return float((np.abs(got - ref) > TOL_ABS + TOL_REL * np.abs(ref)).mean())
+
+
+@pytest.fixture(scope="module")
+def half1(golden_dir):
+    return np.load(os.path.join(golden_dir, "half1_reference.npz"))
+
+
+@pytest.fixture(scope="module")
+def half2(golden_dir):
+    return np.load(os.path.join(golden_dir, "half2_oracle.npz"))
+
+
+# ---- half 1 against the reference's own outputs --------------------------------------------------
+
+@pytest.mark.parametrize("case", ["A", "B"])
+def test_half1_matches_reference_fixture(half1, case):
+    g = {k[len(case) + 1:]: half1[k] for k in half1.files if k.startswith(case + "_")}
+    pts, q, P = g["pts"], g["query_idx"], int(g["P"])
+    radius = list(g["patch_radius"])
+    S = len(radius)
+    # radii: bbdiag * rad, bit-exact (pcpnet_dataset.py:281-282)
+    assert abs(orc.bbdiag_of(pts) - float(g["bbdiag"])) < 1e-12   # stored as radii_abs[0] / radius[0]
+    assert orc.absolute_radii(pts, radius) == list(g["radii_abs"])
+    patches, n_eff, total, nbr = orc.gather_patches(pts, q, radius, P, seed=3627473, return_indices=True)
+    assert np.array_equal(n_eff, g["n_eff"])
+    off = g["nbr_off"]
+    for b in range(len(q)):
+        for s in range(S):
+            ref_set = g["nbr_flat"][off[b * S + s]:off[b * S + s + 1]]
+            assert total[b, s] == len(ref_set)
+            # the float64 leaf predicate, independently of the tree
+            assert np.array_equal(orc.ball_query_bruteforce(pts, int(q[b]), g["radii_abs"][s]), ref_set)
+            mine = patches[b, s * P:(s + 1) * P]
+            ref = g["patches"][b, s * P:(s + 1) * P]
+            if not g["subsampled"][b, s]:
+                assert np.array_equal(nbr[b, s, :len(ref_set)], ref_set)
+                assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32)), "patch not bit-exact"
+            else:
+                # both selections are P-subsets of the same neighbourhood, normalised identically
+                cand = ((pts[ref_set] - pts[q[b]]) / np.float32(g["radii_abs"][s])).astype(np.float32)
+                cand_rows = {r.tobytes() for r in cand}
+                assert all(r.tobytes() in cand_rows for r in ref)
+                assert all(r.tobytes() in cand_rows for r in mine)
+                sel = nbr[b, s]
+                assert len(sel) == P and np.all(np.diff(sel) > 0) and np.isin(sel, ref_set).all()
+            assert np.all(mine[n_eff[b, s]:] == 0)
+
+
+def test_selection_rule_properties():
+    nbr = np.random.RandomState(0).choice(100000, 3000, replace=False)
+    sel = orc.select_subset(nbr, 512, 3627473, 17, 2)
+    assert len(sel) == 512 and np.all(np.diff(sel) > 0) and np.isin(sel, nbr).all()
+    assert np.array_equal(sel, orc.select_subset(nbr[::-1], 512, 3627473, 17, 2))     # order independent
+    assert not np.array_equal(sel, orc.select_subset(nbr, 512, 3627473, 17, 3))        # scale enters the key
+    assert not np.array_equal(sel, orc.select_subset(nbr, 512, 3627474, 17, 2))        # seed enters the key
+    keys = orc.selection_keys(3627473, 17, 2, np.sort(nbr)).astype(np.int64)
+    kth = np.sort(keys)[511]
+    assert np.all(keys[np.isin(np.sort(nbr), sel)] <= kth)
+    small = np.arange(40)
+    assert np.array_equal(orc.select_subset(small[::-1], 64, 1, 2, 0), small)          # no subsample needed
+
+
+def test_philox_known_answers_and_c_port():
+    # Random123 known-answer vectors for philox4x32-10
+    assert [int(x) for x in orc.philox4x32_10(0, 0, 0, 0, 0, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    assert [int(x) for x in orc.philox4x32_10(f, f, f, f, f, f)] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert [int(x) for x in orc.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)] == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    nbr = np.arange(1000, 1200)
+    for seed, c, s in [(3627473, 17, 0), (3627473, 17, 3), ((9 << 32) | 5, 99999, 6)]:
+        assert np.array_equal(orc.selection_keys(seed, c, s, nbr), c_oracle.selection_keys(seed, c, s, nbr))
+
+
+# ---- half 2 ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["g3", "g8", "g8p512", "gen"])
+def test_half2_fixture_regression_and_c_port(half2, case):
+    pts, ne, w, mu, sg = (half2["%s_%s" % (case, k)] for k in ("points", "n_eff", "w", "mu", "sigma"))
+    fv = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False, n_original_points=ne)
+    assert np.allclose(fv, half2[case + "_fv_n_est"], rtol=0, atol=1e-7)
+    plain = orc.get_3dmfv(pts, w, mu, sg, flatten=False)
+    assert np.allclose(plain, half2[case + "_fv_plain"], rtol=0, atol=1e-7)
+    # float64 restatement written independently
+    assert np.abs(fv - orc.get_3dmfv_n_est_f64(pts, w, mu, sg, ne, masked=True)).max() < 1e-6
+    assert np.abs(plain - orc.get_3dmfv_n_est_f64(pts, w, mu, sg, None, masked=False)).max() < 1e-6
+    # C port
+    assert frac_outside(c_oracle.get_3dmfv(pts, w, mu, sg, ne, masked=True), fv) == 0.0
+    assert frac_outside(c_oracle.get_3dmfv(pts, w, mu, sg, None, masked=False), plain) == 0.0
+    # flatten=True is the channel-major flattening of flatten=False
+    flat = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=True, n_original_points=ne)
+    assert np.array_equal(flat, fv.reshape(len(pts), -1))
+    # every channel is L2-normalised over the Gaussians (or identically zero)
+    nrm = np.sqrt((fv.astype(np.float64) ** 2).sum(-1))
+    assert np.all((np.abs(nrm - 1) < 1e-5) | (nrm == 0))
+
+
+def test_mask_off_by_one_and_padding_semantics():
+    """tf_util.py:696 masks r > n_eff: slot n_eff (a zero pad) takes part, slot n_eff+1 does not;
+    masked slots feed exact zeros into max/min."""
+    w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([3] * 3, 0.11))
+    rng = np.random.RandomState(3)
+    P, ne = 16, 6
+    pts = np.zeros((1, P, 3), np.float32)
+    pts[0, :ne] = rng.uniform(-0.5, 0.5, (ne, 3))
+    base = orc.get_3dmfv_n_est(pts, w, mu, sg, n_original_points=[ne])
+    p2 = pts.copy(); p2[0, ne + 1] = 0.3
+    assert np.array_equal(base, orc.get_3dmfv_n_est(p2, w, mu, sg, n_original_points=[ne]))
+    p3 = pts.copy(); p3[0, ne] = 0.3
+    assert not np.array_equal(base, orc.get_3dmfv_n_est(p3, w, mu, sg, n_original_points=[ne]))
+    fv = base.reshape(20, -1)
+    assert np.all(fv[[0, 2, 3, 4, 11, 12, 13]] >= 0) and np.all(fv[[5, 6, 7, 14, 15, 16]] <= 0)
+    with pytest.raises(ValueError):
+        orc.get_3dmfv_n_est(pts, w, mu, sg)
+
+
+def test_mups_layout_and_c_port():
+    """models/experts_n_est.py:71-76: MuPS[b,i,j,k,s*20+c] = fv_s[b,c,(i*res+j)*res+k]."""
+    res, P, S, B = 3, 16, 3, 5
+    w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([res] * 3, 0.11))
+    rng = np.random.RandomState(5)
+    pts = rng.uniform(-0.6, 0.6, (B, S * P, 3)).astype(np.float32)
+    ne = rng.randint(1, P + 1, (B, S)).astype(np.int32)
+    for b in range(B):
+        for s in range(S):
+            pts[b, s * P + ne[b, s]:(s + 1) * P] = 0
+    mups = orc.mups_assemble(pts, w, mu, sg, ne, S)
+    assert mups.shape == (B, res, res, res, 20 * S)
+    for s in range(S):
+        fv = orc.get_3dmfv_n_est(pts[:, s * P:(s + 1) * P], w, mu, sg, flatten=False, n_original_points=ne[:, s])
+        for c in (0, 7, 19):
+            assert np.array_equal(mups[..., s * 20 + c].reshape(B, -1), fv[:, c, :])
+    assert frac_outside(c_oracle.mups(pts, ne, w, mu, sg, S), mups) == 0.0
+    # the grid: x slowest (np.mgrid), cell centres, sigma = sqrt(variance)
+    w8, mu8, sg8 = orc.gmm_feed(*orc.get_3d_grid_gmm([8] * 3, 0.0156))
+    assert np.allclose(mu8[0], [-0.875] * 3) and np.allclose(mu8[1], [-0.875, -0.875, -0.625])
+    assert np.allclose(mu8[64], [-0.625, -0.875, -0.875]) and np.allclose(sg8, 0.1249, atol=1e-4) and np.allclose(w8, 1 / 512)
+
+
+def test_c_port_on_realistic_patches():
+    """numpy restatement vs C port on patches of a PCPNet-shape cloud.  Sum channels whose value
+    is a near-complete fp32 cancellation are ill-conditioned under the signed square root, so a
+    ~1e-6 fraction of elements may leave the 1e-5/1e-6 band between ANY two fp32 evaluations
+    ('Tolerance'); bound that fraction and the size of the excursions."""
+    pts = orc.synthetic_cloud(30000, cloud_id=2)
+    radius = [0.01, 0.03, 0.05, 0.07]
+    q = np.arange(0, 30000, 2000)
+    patches, n_eff, _ = orc.gather_patches(pts, q, radius, 512)
+    w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([8] * 3, 0.0156))
+    a = orc.mups_assemble(patches, w, mu, sg, n_eff, 4)
+    c = c_oracle.mups(patches, n_eff, w, mu, sg, 4)
+    assert frac_outside(c, a) < 2e-5
+    assert np.abs(c - a).max() < 1e-4
