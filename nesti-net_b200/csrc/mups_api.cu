@@ -220,6 +220,20 @@ int mups_gmm_create(mups_gmm** out, const float* w, const float* mu, const float
             sep = mu[3 * g] == mu[3 * (i * ny * nz)] && mu[3 * g + 1] == mu[3 * (j * nz) + 1] && mu[3 * g + 2] == mu[3 * k + 2] &&
                   sigma[3 * g] == sigma[0] && sigma[3 * g + 1] == sigma[1] && sigma[3 * g + 2] == sigma[2] && w[g] == w[0];
         }
+        // the fast path's guard assumes that inside the lattice hull some centre is always within
+        // 5 sigma per axis: consecutive lattice coordinates at most 10 sigma apart, ascending
+        for (int ax = 0; sep && ax < 3; ++ax) {
+            const int na = ax == 0 ? nx : (ax == 1 ? ny : nz);
+            const int stride = ax == 0 ? ny * nz : (ax == 1 ? nz : 1);
+            for (int t = 1; sep && t < na; ++t) {
+                const float gap = mu[3 * (t * stride) + ax] - mu[3 * ((t - 1) * stride) + ax];
+                sep = gap > 0.f && gap <= 10.0f * sigma[ax];
+            }
+            if (sep) {
+                gm->guard_lo[ax] = mu[ax] - 5.0f * sigma[ax];
+                gm->guard_hi[ax] = mu[3 * ((na - 1) * stride) + ax] + 5.0f * sigma[ax];
+            }
+        }
         gm->separable = sep ? 1 : 0;
         if (sep) {
             gm->res[0] = nx; gm->res[1] = ny; gm->res[2] = nz;
@@ -263,7 +277,14 @@ int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_e
                  "(the reference fails on n_original_points=None, tf_util.py:665)");
     MUPS_REQUIRE((flags & ~(MUPS_FLAG_MASKED | MUPS_LAYOUT_CHANNEL | MUPS_FLAG_NO_FASTPATH)) == 0, "mups_3dmfv: unknown flags 0x%x", flags);
     if (int rc = check_device(gmm->device, "mups_3dmfv")) return rc;
-    return launch_3dmfv(gmm, patches_dev, n_eff_dev, B, S, P, flags, out_dev, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // stream-ordered scratch for the fast path's fallback worklist (1 counter + one id per (query, scale))
+    int* work = nullptr;
+    if (gmm->separable && !(flags & MUPS_FLAG_NO_FASTPATH) && B > 0)
+        MUPS_CUDA_TRY(cudaMallocAsync((void**)&work, sizeof(int) * (size_t)(B * S + 1), st));
+    const int rc = launch_3dmfv(gmm, patches_dev, n_eff_dev, B, S, P, flags, out_dev, work, st);
+    if (work) cudaFreeAsync(work, st);
+    return rc;
 }
 
 int mups_features(const mups_index* index, const mups_gmm* gmm, const int64_t* query_idx_dev, int64_t B,

@@ -88,6 +88,7 @@ struct mups_gmm {
     // separable path: per axis lattice coordinates and 1/sigma (device, [3][max res] floats) + uniform weight
     float* axis_mu = nullptr;   // [3*64]
     float axis_isig[3] = {0, 0, 0};
+    float guard_lo[3] = {0, 0, 0}, guard_hi[3] = {0, 0, 0};   // lattice hull widened by 5 sigma per axis
     float w_uniform = 0;
 };
 
@@ -99,7 +100,7 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
                       uint64_t seed, int32_t* nbr_idx, int32_t* nbr_total, float* patches, int32_t* n_eff,
                       cudaStream_t st);
 int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff, int64_t B, int S, int P,
-                 uint32_t flags, float* out, cudaStream_t st);
+                 uint32_t flags, float* out, int* work, cudaStream_t st);
 
 // ---- small device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t morton_expand(uint32_t v) {  // 10 bits -> every third bit

@@ -2,14 +2,24 @@
 // get_3dmfv_n_est (reference utils/tf_util.py:655-753), get_3dmfv (:578-652) and the MuPS
 // assembly (models/experts_n_est.py:59-76).
 //
-// One CTA per (query, scale).  The patch (<= P x 3 fp32) and the GMM are staged in shared memory;
-// phase 1 computes every point's posterior normaliser sum_g w_g p_g(x) (thread per point, Gaussian
-// parameters broadcast from shared memory); phase 2 is thread-per-Gaussian: the 20 running
-// reductions (7 sums, 7 max, 6 min) of each owned Gaussian live in registers while the points
-// are broadcast from shared memory; the epilogue applies /n_eff, the signed square root and the
-// per-channel L2 norm over the Gaussians (a CTA-wide reduction) and stores straight into the
-// [B, res, res, res, 20*S] tensor.  FP32-issue/MUFU bound (no tensor cores: the K=3 contraction
-// is not a GEMM); HBM traffic is the 80*G bytes written per (query, scale).
+// Two kernels, one CTA per (query, scale), FP32-issue bound (no tensor cores: the K=3 contraction
+// is not a GEMM; HBM traffic is just the 80*G bytes written per (query, scale)):
+//
+//  * stats_separable_kernel -- the lattice GMM of get_3d_grid_gmm (tensor-product means, one sigma
+//    per axis, uniform w) factorises: Q(n,(i,j,k)) = qx(n,i) qy(n,j) qz(n,k).  Per tile of points the
+//    per-axis factors (q, q t, q (t^2-1)) are staged in shared memory (3*res exps per point instead
+//    of res^3), then every thread owns 4 Gaussians along z and keeps their 20 running reductions in
+//    registers, consuming two points per step: products and sums as packed f32x2, max/min folded
+//    with 3-input FMNMX3.  Patches whose points leave the lattice's 5-sigma box (where the
+//    reference's single exp would underflow differently) are pushed to a worklist and redone by
+//    the general kernel, so the fast path never changes semantics.
+//  * stats_general_kernel   -- arbitrary (w, mu, sigma): phase 1 computes every point's posterior
+//    normaliser (thread per point, Gaussians broadcast from shared memory), phase 2 is thread per
+//    Gaussian with the 20 reductions in registers.
+//
+// Both end with the same epilogue: masked-slot zeros, scale factors, /n_eff, signed square root,
+// per-channel L2 norm over the Gaussians (CTA-wide reduction), direct store into
+// [B, res, res, res, 20*S] (or channel-major).
 #include "mups_common.cuh"
 
 namespace mups {
@@ -24,12 +34,53 @@ struct StatsArgs {
     int S, P;
     uint32_t flags;
     float* out;
+    // separable lattice
+    const float* axis_mu;      // [3][64]
+    float isig[3];
+    float w_uniform;
+    int res[3];
+    int shift[3];              // log2(res)
+    float guard_lo[3], guard_hi[3];   // coordinates outside [lattice - 5 sigma, lattice + 5 sigma] -> general kernel
+    // fallback worklist (separable kernel pushes, general kernel pops)
+    int* worklist;             // [B*S] item ids
+    int* work_count;           // [1]
+    int use_worklist;          // general kernel: take items from the worklist
 };
+
+typedef unsigned long long u64;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 __device__ __forceinline__ float signed_sqrt(float v) {   // tf.sign(x) * tf.pow(tf.abs(x), 0.5)
@@ -38,6 +89,81 @@ __device__ __forceinline__ float signed_sqrt(float v) {   // tf.sign(x) * tf.pow
 }
 
 constexpr float kNegHalfLog2e = -0.72134752044448170368f;   // -0.5 * log2(e)
+
+// Shared per-Gaussian epilogue: v[0..19] hold the raw reductions over the unmasked slots
+// (v[0] = max d_pi, v[1] = sum d_pi already in d_pi units).  Applies the masked slots' exact zeros
+// (tf_util.py:698,703), the 1/sqrt(w), 1/sqrt(2w) factors (:715,:719), /n_eff (:728-730) and the
+// signed square root (:733-736); accumulates the squares for the channel norms.
+__device__ __forceinline__ void finalize_gaussian(float v[20], bool any_masked, float smu, float ssg, float npts,
+                                                  bool valid, float sq[20]) {
+    if (any_masked) {
+        v[0] = fmaxf(v[0], 0.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[2 + k] = fmaxf(v[2 + k], 0.f); v[5 + k] = fminf(v[5 + k], 0.f);
+            v[11 + k] = fmaxf(v[11 + k], 0.f); v[14 + k] = fminf(v[14 + k], 0.f);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+        float x = v[c];
+        if (c >= 2) x *= (c < 11 ? smu : ssg);
+        x = signed_sqrt(x / npts);
+        v[c] = x;
+        if (valid) sq[c] = fmaf(x, x, sq[c]);
+    }
+}
+
+// tf.nn.l2_normalize over the Gaussians per channel: inv_norm[c] = rsqrt(max(sum_g x^2, 1e-12)) (:739-741)
+template <int NT>
+__device__ __forceinline__ void channel_norms(const float sq[20], float* red /*[NT/32][20]*/, float* inv_norm /*[20]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < 20; ++c) {
+        float x = sq[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[warp * 20 + c] = x;
+    }
+    __syncthreads();
+    if (tid < 20) {
+        float x = 0.f;
+        for (int w = 0; w < NT / 32; ++w) x += red[w * 20 + tid];
+        inv_norm[tid] = 1.0f / sqrtf(fmaxf(x, 1e-12f));
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void store_gaussian(const StatsArgs& a, int64_t b, int s, int g, const float v[20],
+                                               const float* scale /* nullptr: raw */) {
+    const int S = a.S, G = a.G;
+    if (a.flags & MUPS_LAYOUT_CHANNEL) {
+#pragma unroll
+        for (int c = 0; c < 20; ++c) a.out[((b * S + s) * 20 + c) * (int64_t)G + g] = scale ? v[c] * scale[c] : v[c];
+    } else {
+        float4* o = reinterpret_cast<float4*>(a.out + ((b * G + g) * (int64_t)S + s) * 20);
+#pragma unroll
+        for (int c = 0; c < 20; c += 4)
+            o[c >> 2] = scale ? make_float4(v[c] * scale[c], v[c + 1] * scale[c + 1], v[c + 2] * scale[c + 2], v[c + 3] * scale[c + 3])
+                              : make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+}
+
+__device__ __forceinline__ void rescale_gaussian(const StatsArgs& a, int64_t b, int s, int g, const float* scale) {
+    const int S = a.S, G = a.G;
+    if (a.flags & MUPS_LAYOUT_CHANNEL) {
+#pragma unroll
+        for (int c = 0; c < 20; ++c) a.out[((b * S + s) * 20 + c) * (int64_t)G + g] *= scale[c];
+    } else {
+        float* o = a.out + ((b * G + g) * (int64_t)S + s) * 20;
+#pragma unroll
+        for (int c = 0; c < 20; ++c) o[c] *= scale[c];
+    }
+}
+
+// =====================================================================================================
+// general kernel
+// =====================================================================================================
 
 // w_g * p_g(x) = 2^(c_g - 0.5*log2(e) * sum_k t_k^2), c_g = log2(w_g * prefactor_g)
 __device__ __forceinline__ float weighted_pdf(float x, float y, float z, const float4& A, const float4& Bq, float cg) {
@@ -54,201 +180,380 @@ __global__ void __launch_bounds__(NT) stats_general_kernel(const StatsArgs a) {
     float4* gB = gA + G;
     float4* pt = gB + G;
     float* part = reinterpret_cast<float*>(pt + P);       // [max(NT, P)]
-    float* red = part + (NT > P ? NT : P);                // [NT/32][20] then inv[20]
-    float* inv_norm = red + (NT / 32) * 20;
+    float* red = part + (NT > P ? NT : P);                // [NT/32][20]
+    float* inv_norm = red + (NT / 32) * 20;               // [20]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t b = blockIdx.x / S;
-    const int s = blockIdx.x % S;
+    const int tid = threadIdx.x;
+    const bool masked = (a.flags & MUPS_FLAG_MASKED) != 0;
+    for (int i = tid; i < G; i += NT) { gA[i] = __ldg(a.A + i); gB[i] = __ldg(a.Bv + i); }
+
+    const int n_items = a.use_worklist ? *a.work_count : (int)gridDim.x;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int item = a.use_worklist ? a.worklist[it] : it;
+        const int64_t b = item / S;
+        const int s = item % S;
+        int n_eff = masked ? a.n_eff[b * S + s] : P;
+        if (n_eff < 0) n_eff = 0;
+        const int m = masked ? min(n_eff + 1, P) : P;     // slots with r > n_eff are masked (tf_util.py:696)
+        const bool any_masked = m < P;
+        {
+            const float* src = a.patches + (b * S + s) * (int64_t)P * 3;
+            for (int n = tid; n < m; n += NT)
+                pt[n] = make_float4(__ldg(src + 3 * n), __ldg(src + 3 * n + 1), __ldg(src + 3 * n + 2), 0.f);
+        }
+        __syncthreads();
+
+        // ---- phase 1: normaliser per point ------------------------------------------------------------
+        {
+            int PT = 1;
+            while (PT < m && PT < NT) PT <<= 1;
+            const int chunks = NT / PT;
+            const int pl = tid & (PT - 1), ch = tid / PT;
+            const int Gc = (G + chunks - 1) / chunks;
+            const int g0 = ch * Gc, g1 = min(G, g0 + Gc);
+            for (int n0 = pl; n0 < m; n0 += 2 * PT) {
+                const int n1 = n0 + PT;
+                const bool has1 = n1 < m;
+                const float4 p0 = pt[n0];
+                const float4 p1 = has1 ? pt[n1] : p0;
+                float acc0 = 0.f, acc1 = 0.f;
+                for (int g = g0; g < g1; ++g) {
+                    const float4 A = gA[g], Bq = gB[g];
+                    const float cg = masked ? A.w : Bq.w;
+                    acc0 += weighted_pdf(p0.x, p0.y, p0.z, A, Bq, cg);
+                    acc1 += weighted_pdf(p1.x, p1.y, p1.z, A, Bq, cg);
+                }
+                part[ch * m + n0] = acc0;
+                if (has1) part[ch * m + n1] = acc1;
+            }
+            __syncthreads();
+            for (int n = tid; n < m; n += NT) {
+                float d = 0.f;
+                for (int c = 0; c < chunks; ++c) d += part[c * m + n];
+                pt[n].w = 1.0f / d;
+            }
+            __syncthreads();
+        }
+
+        // ---- phase 2: 20 reductions per Gaussian ------------------------------------------------------
+        const float npts = masked ? (float)n_eff : 1.0f;                     // tf_util.py:722-730
+        const float inv_static = masked ? 1.0f : 1.0f / (float)P;            // get_3dmfv folds 1/n_points into the scales
+        const int tiles = (G + GPT * NT - 1) / (GPT * NT);
+        float sq[20];
+#pragma unroll
+        for (int c = 0; c < 20; ++c) sq[c] = 0.f;
+        float v[GPT][20];
+
+        for (int tile = 0; tile < tiles; ++tile) {
+            float mux[GPT], muy[GPT], muz[GPT], isx[GPT], isy[GPT], isz[GPT], cg[GPT], pis[GPT], pio[GPT];
+#pragma unroll
+            for (int i = 0; i < GPT; ++i) {
+                const int g = (tile * GPT + i) * NT + tid;
+                const int gc = g < G ? g : G - 1;
+                const float4 A = gA[gc], Bq = gB[gc], Cq = __ldg(a.C + gc);
+                mux[i] = A.x; muy[i] = A.y; muz[i] = A.z;
+                isx[i] = Bq.x; isy[i] = Bq.y; isz[i] = Bq.z;
+                cg[i] = masked ? A.w : Bq.w;
+                pis[i] = Cq.y * inv_static;          // 1/sqrt(w) [/P]
+                pio[i] = -Cq.x * pis[i];             // d_pi = (Q - w) * pis   (tf_util.py:710 / :618)
+#pragma unroll
+                for (int c = 0; c < 20; ++c) v[i][c] = 0.f;
+                v[i][0] = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    v[i][2 + k] = -INFINITY; v[i][5 + k] = INFINITY;
+                    v[i][11 + k] = -INFINITY; v[i][14 + k] = INFINITY;
+                }
+            }
+            for (int n = 0; n < m; ++n) {
+                const float4 p = pt[n];
+#pragma unroll
+                for (int i = 0; i < GPT; ++i) {
+                    const float tx = (p.x - mux[i]) * isx[i], ty = (p.y - muy[i]) * isy[i], tz = (p.z - muz[i]) * isz[i];
+                    const float ss = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
+                    const float Q = ex2_approx(fmaf(ss, kNegHalfLog2e, cg[i])) * p.w;
+                    const float d = fmaf(Q, pis[i], pio[i]);
+                    v[i][0] = fmaxf(v[i][0], d);
+                    v[i][1] += d;
+                    const float ax = Q * tx, ay = Q * ty, az = Q * tz;                        // d_mu  (:714)
+                    v[i][2] = fmaxf(v[i][2], ax); v[i][3] = fmaxf(v[i][3], ay); v[i][4] = fmaxf(v[i][4], az);
+                    v[i][5] = fminf(v[i][5], ax); v[i][6] = fminf(v[i][6], ay); v[i][7] = fminf(v[i][7], az);
+                    v[i][8] += ax; v[i][9] += ay; v[i][10] += az;
+                    const float bx = fmaf(ax, tx, -Q), by = fmaf(ay, ty, -Q), bz = fmaf(az, tz, -Q);   // d_sigma (:718)
+                    v[i][11] = fmaxf(v[i][11], bx); v[i][12] = fmaxf(v[i][12], by); v[i][13] = fmaxf(v[i][13], bz);
+                    v[i][14] = fminf(v[i][14], bx); v[i][15] = fminf(v[i][15], by); v[i][16] = fminf(v[i][16], bz);
+                    v[i][17] += bx; v[i][18] += by; v[i][19] += bz;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < GPT; ++i) {
+                const int g = (tile * GPT + i) * NT + tid;
+                const bool valid = g < G;
+                const float4 Cq = __ldg(a.C + (valid ? g : G - 1));
+                finalize_gaussian(v[i], any_masked, Cq.y * inv_static, Cq.z * inv_static, npts, valid, sq);
+                if (tiles > 1 && valid) store_gaussian(a, b, s, g, v[i], nullptr);   // raw; rescaled below
+            }
+        }
+
+        channel_norms<NT>(sq, red, inv_norm);
+
+        if (tiles == 1) {
+#pragma unroll
+            for (int i = 0; i < GPT; ++i) {
+                const int g = i * NT + tid;
+                if (g < G) store_gaussian(a, b, s, g, v[i], inv_norm);
+            }
+        } else {
+            // each thread rescales the raw values it wrote itself (same thread: no fence needed)
+            for (int tile = 0; tile < tiles; ++tile) {
+#pragma unroll
+                for (int i = 0; i < GPT; ++i) {
+                    const int g = (tile * GPT + i) * NT + tid;
+                    if (g < G) rescale_gaussian(a, b, s, g, inv_norm);
+                }
+            }
+        }
+        __syncthreads();   // pt / part / red are reused by the next item
+    }
+}
+
+// =====================================================================================================
+// separable (lattice) kernel
+// =====================================================================================================
+
+constexpr int kSepThreads = 128;
+constexpr int kSepKPT = 4;              // Gaussians per thread, consecutive along z
+constexpr int kSepTilePoints = 128;     // points staged per tile (64 point pairs)
+
+__device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 2^-23 (PTX ISA)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Shared-memory factor tables of one tile, per axis a with n_a lattice points:
+//   FA[a][pp][i] = float4(q(n0,i), q(n1,i), qt(n0,i), qt(n1,i))       pp = point pair (n0 = 2pp, n1 = 2pp+1)
+//   FB[a][pp][i] = float2(q(t^2-1)(n0,i), q(t^2-1)(n1,i))
+// A thread fetches both points' factors as packed f32x2 operands with one LDS.128 + one LDS.64 per
+// axis entry; consecutive lattice indices are consecutive 16 B / 8 B words, so a warp's loads
+// (<= 8 distinct j, <= 4 distinct i, one k-quad) are bank-conflict free.
+template <int MINB, bool PACKED_SUMS>
+__global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(const StatsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NT = kSepThreads, TPP = kSepTilePoints / 2;
+    const int nx = a.res[0], ny = a.res[1], nz = a.res[2];
+    float4* FA[3];
+    float2* FB[3];
+    FA[0] = reinterpret_cast<float4*>(smem_raw);
+    FA[1] = FA[0] + TPP * nx;
+    FA[2] = FA[1] + TPP * ny;
+    FB[0] = reinterpret_cast<float2*>(FA[2] + TPP * nz);
+    FB[1] = FB[0] + TPP * nx;
+    FB[2] = FB[1] + TPP * ny;
+    float* lat = reinterpret_cast<float*>(FB[2] + TPP * nz);   // [3][64] lattice coordinates
+    float* red = lat + 3 * 64;                                 // [NT/32][20]
+    float* inv_norm = red + (NT / 32) * 20;                    // [20] (+12 pad)
+    float* coords = inv_norm + 32;                             // [3*P] the patch, staged once (coalesced)
+    __shared__ int s_fallback;
+
+    const int tid = threadIdx.x;
+    const int S = a.S, P = a.P;
+    const int item = blockIdx.x;
+    const int64_t b = item / S;
+    const int s = item % S;
     const bool masked = (a.flags & MUPS_FLAG_MASKED) != 0;
     int n_eff = masked ? a.n_eff[b * S + s] : P;
     if (n_eff < 0) n_eff = 0;
-    const int m = masked ? min(n_eff + 1, P) : P;         // slots with r > n_eff are masked (tf_util.py:696)
+    const int m = masked ? min(n_eff + 1, P) : P;       // slots with r > n_eff are masked (tf_util.py:696)
     const bool any_masked = m < P;
+    const float* src = a.patches + (b * S + s) * (int64_t)P * 3;
 
-    for (int i = tid; i < G; i += NT) { gA[i] = __ldg(a.A + i); gB[i] = __ldg(a.Bv + i); }
-    {
-        const float* src = a.patches + (b * S + s) * (int64_t)P * 3;
-        for (int n = tid; n < m; n += NT)
-            pt[n] = make_float4(__ldg(src + 3 * n), __ldg(src + 3 * n + 1), __ldg(src + 3 * n + 2), 0.f);
-    }
-    __syncthreads();
+    for (int i = tid; i < 3 * 64; i += NT) lat[i] = __ldg(a.axis_mu + i);
+    for (int i = tid; i < 3 * m; i += NT) coords[i] = __ldg(src + i);
+    if (tid == 0) s_fallback = 0;
 
-    // ---- phase 1: normaliser per point ------------------------------------------------------------
-    {
-        int PT = 1;
-        while (PT < m && PT < NT) PT <<= 1;
-        const int chunks = NT / PT;
-        const int pl = tid & (PT - 1), ch = tid / PT;
-        const int Gc = (G + chunks - 1) / chunks;
-        const int g0 = ch * Gc, g1 = min(G, g0 + Gc);
-        for (int n0 = pl; n0 < m; n0 += 2 * PT) {
-            const int n1 = n0 + PT;
-            const bool has1 = n1 < m;
-            const float4 p0 = pt[n0];
-            const float4 p1 = has1 ? pt[n1] : p0;
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int g = g0; g < g1; ++g) {
-                const float4 A = gA[g], Bq = gB[g];
-                const float cg = masked ? A.w : Bq.w;
-                acc0 += weighted_pdf(p0.x, p0.y, p0.z, A, Bq, cg);
-                acc1 += weighted_pdf(p1.x, p1.y, p1.z, A, Bq, cg);
-            }
-            part[ch * m + n0] = acc0;
-            if (has1) part[ch * m + n1] = acc1;
-        }
-        __syncthreads();
-        for (int n = tid; n < m; n += NT) {
-            float d = 0.f;
-            for (int c = 0; c < chunks; ++c) d += part[c * m + n];
-            pt[n].w = 1.0f / d;
-        }
-        __syncthreads();
-    }
+    const float w = a.w_uniform;
+    const float rsw = 1.0f / sqrtf(w), rs2w = 1.0f / sqrtf(2.0f * w);
+    const float inv_static = masked ? 1.0f : 1.0f / (float)P;           // get_3dmfv folds 1/n_points into the scales
+    const float inv_npts = masked ? 1.0f / (float)n_eff : 1.0f;         // tf_util.py:722-730
+    const float pis = rsw * inv_static, smu = rsw * inv_static, ssg = rs2w * inv_static;
 
-    // ---- phase 2: 20 reductions per Gaussian ------------------------------------------------------
-    const float npts = masked ? (float)n_eff : 1.0f;                     // tf_util.py:722-730
-    const float inv_static = masked ? 1.0f : 1.0f / (float)P;            // get_3dmfv folds 1/n_points into the scales
-    const int tiles = (G + GPT * NT - 1) / (GPT * NT);
-    const bool layout_channel = (a.flags & MUPS_LAYOUT_CHANNEL) != 0;
+    const int nzq = nz / kSepKPT;
+    const int nxy = nx * ny;
+    const int tasks = nxy * nzq;
+    const int groups = (tasks + NT - 1) / NT;
     float sq[20];
 #pragma unroll
     for (int c = 0; c < 20; ++c) sq[c] = 0.f;
-    float v[GPT][20];
+    float v[kSepKPT][20];
+    __syncthreads();
 
-    for (int tile = 0; tile < tiles; ++tile) {
-        float mux[GPT], muy[GPT], muz[GPT], isx[GPT], isy[GPT], isz[GPT], cg[GPT], pis[GPT], pio[GPT];
-        bool valid[GPT];
+    for (int group = 0; group < groups; ++group) {
+        // task -> (k-quad, i, j) with j fastest: a warp spans <= 8 j, <= 4 i and (nx*ny >= 32) one k-quad
+        const int task = group * NT + tid;
+        const bool valid = task < tasks;
+        const int tk = valid ? task : 0;
+        const int j = tk % ny, i = (tk / ny) % nx, kq = tk / nxy;
+        const int k0 = kq * kSepKPT;
+
+        u64 sm[kSepKPT][7];       // packed (even point, odd point) partial sums
+        float ss[kSepKPT][7];     // or scalar sums (fewer registers: one more CTA per SM)
+        float mx[kSepKPT][7], mn[kSepKPT][6];
 #pragma unroll
-        for (int i = 0; i < GPT; ++i) {
-            const int g = (tile * GPT + i) * NT + tid;
-            valid[i] = g < G;
-            const int gc = valid[i] ? g : G - 1;
-            const float4 A = gA[gc], Bq = gB[gc], Cq = __ldg(a.C + gc);
-            mux[i] = A.x; muy[i] = A.y; muz[i] = A.z;
-            isx[i] = Bq.x; isy[i] = Bq.y; isz[i] = Bq.z;
-            cg[i] = masked ? A.w : Bq.w;
-            pis[i] = Cq.y * inv_static;          // 1/sqrt(w) [/P]
-            pio[i] = -Cq.x * pis[i];             // d_pi = (Q - w) * pis
+        for (int g = 0; g < kSepKPT; ++g) {
 #pragma unroll
-            for (int c = 0; c < 20; ++c) v[i][c] = 0.f;
-            v[i][0] = -INFINITY;
+            for (int c = 0; c < 7; ++c) { sm[g][c] = 0ull; ss[g][c] = 0.f; mx[g][c] = -INFINITY; }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) mn[g][c] = INFINITY;
+        }
+
+        for (int tile0 = 0; tile0 < m; tile0 += kSepTilePoints) {
+            const int tile_pts = min(kSepTilePoints, m - tile0);
+            const int npairs = (tile_pts + 1) >> 1;
+            // ---- stage the per-axis factors of this tile: one lane per (point, lattice index) ------------
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                const int na = a.res[ax], sh = a.shift[ax];
+                const float isg = a.isig[ax], glo = a.guard_lo[ax], ghi = a.guard_hi[ax];
+                const int total = (2 * npairs) << sh;
+                for (int base = 0; base < total; base += NT) {
+                    const int idx = base + tid;
+                    const int li = idx & (na - 1);
+                    const int nl = idx >> sh;
+                    const int n = tile0 + nl;
+                    const bool real = n < m;                                // false for the odd tail and idle lanes
+                    const float c = coords[3 * (real ? n : 0) + ax];
+                    const float t = (c - lat[ax * 64 + li]) * isg;
+                    const float e = ex2_approx(kNegHalfLog2e * t * t);
+                    float sum = e;
+                    for (int o = na >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (idx < total) {
+                        const float q = real ? e * __frcp_rn(sum) : 0.f;    // a missing second point contributes exact zeros
+                        const float qa = q * t;
+                        float* fa = reinterpret_cast<float*>(FA[ax] + ((nl >> 1) << sh) + li);
+                        fa[nl & 1] = q;
+                        fa[2 + (nl & 1)] = qa;
+                        reinterpret_cast<float*>(FB[ax] + ((nl >> 1) << sh) + li)[nl & 1] = fmaf(qa, t, -q);
+                        if (real && !(c >= glo && c <= ghi)) s_fallback = 1;   // outside the 5-sigma box (or NaN)
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_fallback) break;
+
+            // ---- 20 reductions x 4 Gaussians, two points per step -------------------------------------------
+            if (valid) {
+                const float4* pxa = FA[0] + i;
+                const float4* pya = FA[1] + j;
+                const float4* pza = FA[2] + k0;
+                const float2* pxb = FB[0] + i;
+                const float2* pyb = FB[1] + j;
+                const float2* pzb = FB[2] + k0;
+#pragma unroll 1
+                for (int pp = 0; pp < npairs; ++pp, pxa += nx, pya += ny, pza += nz, pxb += nx, pyb += ny, pzb += nz) {
+                    const float4 fx = *pxa, fy = *pya;
+                    const float2 bx = *pxb, by = *pyb;
+                    const u64 qx = pack2(fx.x, fx.y), ax_ = pack2(fx.z, fx.w), bx_ = pack2(bx.x, bx.y);
+                    const u64 qy = pack2(fy.x, fy.y), ay_ = pack2(fy.z, fy.w), by_ = pack2(by.x, by.y);
+                    const u64 u_qq = mul2(qx, qy), u_aq = mul2(ax_, qy), u_qa = mul2(qx, ay_), u_bq = mul2(bx_, qy),
+                              u_qb = mul2(qx, by_);
+#pragma unroll
+                    for (int g = 0; g < kSepKPT; ++g) {
+                        const float4 fz = pza[g];
+                        const float2 bz = pzb[g];
+                        const u64 qz = pack2(fz.x, fz.y), az_ = pack2(fz.z, fz.w), bz_ = pack2(bz.x, bz.y);
+                        u64 t[7];
+                        t[0] = mul2(u_qq, qz);     // Q
+                        t[1] = mul2(u_aq, qz);     // Q t_x
+                        t[2] = mul2(u_qa, qz);     // Q t_y
+                        t[3] = mul2(u_qq, az_);    // Q t_z
+                        t[4] = mul2(u_bq, qz);     // Q (t_x^2 - 1)
+                        t[5] = mul2(u_qb, qz);     // Q (t_y^2 - 1)
+                        t[6] = mul2(u_qq, bz_);    // Q (t_z^2 - 1)
+#pragma unroll
+                        for (int c = 0; c < 7; ++c) {
+                            float lo, hi;
+                            unpack2(t[c], lo, hi);
+                            if (PACKED_SUMS) sm[g][c] = add2(sm[g][c], t[c]);
+                            else ss[g][c] = (ss[g][c] + lo) + hi;
+                            mx[g][c] = fmax3(mx[g][c], lo, hi);
+                            if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo, hi);
+                        }
+                    }
+                }
+            }
+            __syncthreads();   // the factor tables are rewritten by the next tile
+        }
+        if (s_fallback) break;
+
+        // ---- per-Gaussian epilogue (same steps as finalize_gaussian, with fast reciprocal/sqrt) -------------
+#pragma unroll
+        for (int g = 0; g < kSepKPT; ++g) {
+            float sums[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) {
+                float lo, hi;
+                unpack2(sm[g][c], lo, hi);
+                sums[c] = PACKED_SUMS ? lo + hi : ss[g][c];
+            }
+            // d_pi = (Q - w)/sqrt(w): max and sum over the m unmasked slots (tf_util.py:710-712)
+            v[g][0] = (mx[g][0] - w) * pis;
+            v[g][1] = fmaf(-(float)m, w, sums[0]) * pis;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                v[i][2 + k] = -INFINITY; v[i][5 + k] = INFINITY;
-                v[i][11 + k] = -INFINITY; v[i][14 + k] = INFINITY;
+                v[g][2 + k] = mx[g][1 + k] * smu; v[g][5 + k] = mn[g][k] * smu; v[g][8 + k] = sums[1 + k] * smu;
+                v[g][11 + k] = mx[g][4 + k] * ssg; v[g][14 + k] = mn[g][3 + k] * ssg; v[g][17 + k] = sums[4 + k] * ssg;
             }
-        }
-        for (int n = 0; n < m; ++n) {
-            const float4 p = pt[n];
-#pragma unroll
-            for (int i = 0; i < GPT; ++i) {
-                const float tx = (p.x - mux[i]) * isx[i], ty = (p.y - muy[i]) * isy[i], tz = (p.z - muz[i]) * isz[i];
-                const float ss = fmaf(tz, tz, fmaf(ty, ty, tx * tx));
-                const float Q = ex2_approx(fmaf(ss, kNegHalfLog2e, cg[i])) * p.w;
-                const float d = fmaf(Q, pis[i], pio[i]);
-                v[i][0] = fmaxf(v[i][0], d);
-                v[i][1] += d;
-                const float ax = Q * tx, ay = Q * ty, az = Q * tz;
-                v[i][2] = fmaxf(v[i][2], ax); v[i][3] = fmaxf(v[i][3], ay); v[i][4] = fmaxf(v[i][4], az);
-                v[i][5] = fminf(v[i][5], ax); v[i][6] = fminf(v[i][6], ay); v[i][7] = fminf(v[i][7], az);
-                v[i][8] += ax; v[i][9] += ay; v[i][10] += az;
-                const float bx = fmaf(ax, tx, -Q), by = fmaf(ay, ty, -Q), bz = fmaf(az, tz, -Q);
-                v[i][11] = fmaxf(v[i][11], bx); v[i][12] = fmaxf(v[i][12], by); v[i][13] = fmaxf(v[i][13], bz);
-                v[i][14] = fminf(v[i][14], bx); v[i][15] = fminf(v[i][15], by); v[i][16] = fminf(v[i][16], bz);
-                v[i][17] += bx; v[i][18] += by; v[i][19] += bz;
-            }
-        }
-        // per-Gaussian epilogue: masked slots' zeros, scale factors, /n_eff, signed sqrt
-#pragma unroll
-        for (int i = 0; i < GPT; ++i) {
-            const int g = (tile * GPT + i) * NT + tid;
-            const int gc = valid[i] ? g : G - 1;
-            const float4 Cq = __ldg(a.C + gc);
-            const float smu = Cq.y * inv_static, ssg = Cq.z * inv_static;
-            if (any_masked) {
-                v[i][0] = fmaxf(v[i][0], 0.f);
+            if (any_masked) {      // masked slots contribute exact zeros to max / min (tf_util.py:698,703)
+                v[g][0] = fmaxf(v[g][0], 0.f);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    v[i][2 + k] = fmaxf(v[i][2 + k], 0.f); v[i][5 + k] = fminf(v[i][5 + k], 0.f);
-                    v[i][11 + k] = fmaxf(v[i][11 + k], 0.f); v[i][14 + k] = fminf(v[i][14 + k], 0.f);
+                    v[g][2 + k] = fmaxf(v[g][2 + k], 0.f); v[g][5 + k] = fminf(v[g][5 + k], 0.f);
+                    v[g][11 + k] = fmaxf(v[g][11 + k], 0.f); v[g][14 + k] = fminf(v[g][14 + k], 0.f);
                 }
             }
 #pragma unroll
             for (int c = 0; c < 20; ++c) {
-                float x = v[i][c];
-                if (c >= 2) x *= (c < 11 ? smu : ssg);
-                x = signed_sqrt(x / npts);
-                v[i][c] = x;
-                if (valid[i]) sq[c] = fmaf(x, x, sq[c]);
+                const float x = v[g][c] * inv_npts;                         // :728-730
+                const float r = copysignf(sqrt_approx(fabsf(x)), x);        // :733-736 (sign(0) = 0: sqrt(0) = 0)
+                v[g][c] = r;
+                if (valid) sq[c] = fmaf(r, r, sq[c]);
             }
-            if (tiles > 1 && valid[i]) {   // raw values out; rescaled after the norm is known
-                if (layout_channel) {
-#pragma unroll
-                    for (int c = 0; c < 20; ++c) a.out[((b * S + s) * 20 + c) * (int64_t)G + g] = v[i][c];
-                } else {
-                    float* o = a.out + ((b * G + g) * (int64_t)S + s) * 20;
-#pragma unroll
-                    for (int c = 0; c < 20; ++c) o[c] = v[i][c];
-                }
-            }
+            if (groups > 1 && valid) store_gaussian(a, b, s, (i * ny + j) * nz + k0 + g, v[g], nullptr);
         }
     }
 
-    // ---- channel-wise L2 norm over the Gaussians: x * rsqrt(max(sum x^2, 1e-12)) -------------------
-#pragma unroll
-    for (int c = 0; c < 20; ++c) {
-        float x = sq[c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) red[warp * 20 + c] = x;
+    if (s_fallback) {   // uniform: the whole CTA leaves, the general kernel redoes this (query, scale)
+        if (tid == 0) a.worklist[atomicAdd(a.work_count, 1)] = item;
+        return;
     }
-    __syncthreads();
-    if (tid < 20) {
-        float x = 0.f;
-        for (int w = 0; w < NT / 32; ++w) x += red[w * 20 + tid];
-        inv_norm[tid] = 1.0f / sqrtf(fmaxf(x, 1e-12f));
-    }
-    __syncthreads();
 
-    if (tiles == 1) {
+    channel_norms<NT>(sq, red, inv_norm);
+
+    if (groups == 1) {
+        if (tid < tasks) {
+            const int j = tid % ny, i = (tid / ny) % nx, kq = tid / nxy;
 #pragma unroll
-        for (int i = 0; i < GPT; ++i) {
-            const int g = i * NT + tid;
-            if (g >= G) continue;
-            if (layout_channel) {
-#pragma unroll
-                for (int c = 0; c < 20; ++c) a.out[((b * S + s) * 20 + c) * (int64_t)G + g] = v[i][c] * inv_norm[c];
-            } else {
-                float4* o = reinterpret_cast<float4*>(a.out + ((b * G + g) * (int64_t)S + s) * 20);
-#pragma unroll
-                for (int c = 0; c < 20; c += 4)
-                    o[c >> 2] = make_float4(v[i][c] * inv_norm[c], v[i][c + 1] * inv_norm[c + 1],
-                                            v[i][c + 2] * inv_norm[c + 2], v[i][c + 3] * inv_norm[c + 3]);
-            }
+            for (int g = 0; g < kSepKPT; ++g) store_gaussian(a, b, s, (i * ny + j) * nz + kq * kSepKPT + g, v[g], inv_norm);
         }
     } else {
-        // each thread rescales the raw values it wrote itself (same thread: no fence needed)
-        for (int tile = 0; tile < tiles; ++tile) {
+        for (int group = 0; group < groups; ++group) {
+            const int task = group * NT + tid;
+            if (task < tasks) {
+                const int j = task % ny, i = (task / ny) % nx, kq = task / nxy;
 #pragma unroll
-            for (int i = 0; i < GPT; ++i) {
-                const int g = (tile * GPT + i) * NT + tid;
-                if (g >= G) continue;
-                if (layout_channel) {
-#pragma unroll
-                    for (int c = 0; c < 20; ++c) a.out[((b * S + s) * 20 + c) * (int64_t)G + g] *= inv_norm[c];
-                } else {
-                    float* o = a.out + ((b * G + g) * (int64_t)S + s) * 20;
-#pragma unroll
-                    for (int c = 0; c < 20; ++c) o[c] *= inv_norm[c];
-                }
+                for (int g = 0; g < kSepKPT; ++g) rescale_gaussian(a, b, s, (i * ny + j) * nz + kq * kSepKPT + g, inv_norm);
             }
         }
     }
 }
 
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+
 template <int GPT, int NT>
-static int launch_general(const StatsArgs& a, int64_t B, cudaStream_t st) {
+static int launch_general(const StatsArgs& a, int64_t items, int grid, cudaStream_t st) {
     const size_t smem = sizeof(float4) * (2 * (size_t)a.G + a.P) + sizeof(float) * ((NT > a.P ? NT : a.P) + (NT / 32) * 20 + 32);
     if (smem > 220 * 1024) {
         set_error("3dmfv: G=%d, P=%d needs %zu bytes of shared memory", a.G, a.P, smem);
@@ -256,24 +561,68 @@ static int launch_general(const StatsArgs& a, int64_t B, cudaStream_t st) {
     }
     if (smem > 48 * 1024)
         MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_general_kernel<GPT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stats_general_kernel<GPT, NT><<<(unsigned)(B * a.S), NT, smem, st>>>(a);
+    (void)items;
+    stats_general_kernel<GPT, NT><<<(unsigned)grid, NT, smem, st>>>(a);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;
 }
 
+static int dispatch_general(const StatsArgs& a, int64_t items, int grid, cudaStream_t st) {
+    if (a.G <= 128) return launch_general<1, 128>(a, items, grid, st);
+    if (a.G <= 256) return launch_general<1, 256>(a, items, grid, st);
+    return launch_general<2, 256>(a, items, grid, st);
+}
+
+static bool pow2_in(int v, int lo, int hi) { return v >= lo && v <= hi && (v & (v - 1)) == 0; }
+
 int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff, int64_t B, int S, int P,
-                 uint32_t flags, float* out, cudaStream_t st) {
+                 uint32_t flags, float* out, int* work /* [1 + B*S] ints of scratch, or nullptr */, cudaStream_t st) {
     StatsArgs a;
     a.A = gmm->A; a.Bv = gmm->Bv; a.C = gmm->C; a.G = gmm->G;
-    a.patches = patches; a.n_eff = n_eff; a.S = S; a.P = P; a.flags = flags; a.out = out;
+    a.patches = patches; a.n_eff = n_eff; a.S = S; a.P = P; a.flags = flags & ~MUPS_FLAG_NO_FASTPATH; a.out = out;
+    a.axis_mu = gmm->axis_mu;
+    for (int k = 0; k < 3; ++k) {
+        a.isig[k] = gmm->axis_isig[k]; a.res[k] = gmm->res[k];
+        a.guard_lo[k] = gmm->guard_lo[k]; a.guard_hi[k] = gmm->guard_hi[k];
+        a.shift[k] = 0;
+        while ((1 << a.shift[k]) < a.res[k]) ++a.shift[k];
+    }
+    a.w_uniform = gmm->w_uniform;
+    a.worklist = nullptr; a.work_count = nullptr; a.use_worklist = 0;
     if (B == 0) return MUPS_OK;
-    if (B * (int64_t)S > 0x7FFFFFFFll) {
-        set_error("3dmfv: B*S = %lld exceeds the grid limit; split the batch", (long long)(B * S));
+    const int64_t items = B * (int64_t)S;
+    if (items > 0x7FFFFFFFll) {
+        set_error("3dmfv: B*S = %lld exceeds the grid limit; split the batch", (long long)items);
         return MUPS_ERR_UNSUPPORTED;
     }
-    if (a.G <= 128) return launch_general<1, 128>(a, B, st);
-    if (a.G <= 256) return launch_general<1, 256>(a, B, st);
-    return launch_general<2, 256>(a, B, st);
+    // the lattice fast path: power-of-two axes (shuffle reductions), 4 | nz, even P (points are consumed in pairs)
+    const bool fast = gmm->separable && !(flags & MUPS_FLAG_NO_FASTPATH) && work != nullptr && (P % 2 == 0) &&
+                      pow2_in(gmm->res[0], 4, 32) && pow2_in(gmm->res[1], 4, 32) && pow2_in(gmm->res[2], 4, 32);
+    if (!fast) return dispatch_general(a, items, (int)items, st);
+
+    a.work_count = work;
+    a.worklist = work + 1;
+    MUPS_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(int), st));
+    const int TPP = kSepTilePoints / 2;
+    const size_t smem = (size_t)TPP * (a.res[0] + a.res[1] + a.res[2]) * (sizeof(float4) + sizeof(float2)) +
+                        sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
+    const int variant = g_stats_variant.load();
+#define MUPS_LAUNCH_SEP(MINB, PACKED)                                                                               \
+    do {                                                                                                            \
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, PACKED>,                                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+        stats_separable_kernel<MINB, PACKED><<<(unsigned)items, kSepThreads, smem, st>>>(a);                        \
+    } while (0)
+    if (variant == 2) MUPS_LAUNCH_SEP(2, true);
+    else if (variant == 3) MUPS_LAUNCH_SEP(3, true);
+    else if (variant == 5) MUPS_LAUNCH_SEP(3, false);
+    else MUPS_LAUNCH_SEP(4, false);
+#undef MUPS_LAUNCH_SEP
+    MUPS_CHECK_LAUNCH();
+    // patches that left the lattice's 5-sigma box (none for real patches, which live in the unit ball)
+    a.use_worklist = 1;
+    const int grid = (int)(items < 2 * kNumSMs ? items : 2 * kNumSMs);
+    return dispatch_general(a, items, grid, st);
 }
 
 }  // namespace mups
