@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""MuPS benchmark (the driver's contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "Nesti-Net MoE default"): every one of the 100 000 points of
+a synthetic PCPNet-shape cloud is a query; 4 scales (0.01/0.03/0.05/0.07 of the bbox diagonal),
+512-point patches, 8^3 Gaussian grid -> MuPS [100000, 8, 8, 8, 80] fp32 (16.4 GB) per cloud.
+One step = the whole hot path for one such cloud per GPU: index build, ball query + subsample +
+normalise, 3DmFV statistics.  With N GPUs a step covers N clouds (replicated on every rank); the
+query list of each cloud is split into N contiguous shards and rank r computes shard r of every
+cloud into its own slab: per-GPU work is fixed (weak scaling), no collective on the data path.
+
+value  = query points/s, device-timed (CUDA events on the launching stream, max over ranks),
+         cloud already resident in HBM.
+e2e    = the same metric through MuPSPipeline.features_to_host: host cloud in (pinned), MuPS
+         streamed back into pinned host memory, all copies inside the timed region.
+roofline: the statistics kernel against the FP32 issue roof (46 FP32 op-slots + 1
+         exp per unmasked (point, Gaussian) pair), its duration measured live with CUDA events.
+--impl reference: the reference's CPU path on the host cores (scipy cKDTree + the oracle's
+         OpenMP C port of get_3dmfv_n_est; TensorFlow 1.12 cannot be installed) on a bounded
+         sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mups_query_points_per_s"
+UNIT = "query points/s"
+N_POINTS = 100000
+RADIUS = [0.01, 0.03, 0.05, 0.07]
+P = 512
+RES = 8
+VARIANCE = 0.0156            # the reference's command line for an 8^3 grid (train_n_est_w_experts.py:20)
+SEED = 3627473
+N_CLOUDS = 4                 # distinct synthetic clouds cycled through the steps
+OPS_PER_PAIR = 46            # algorithmic FP32 op-slots per unmasked (point, Gaussian) pair
+WORKLOAD = ("configs[1]: Nesti-Net MoE default - 4 scales (0.01/0.03/0.05/0.07), 512-pt patches, 8^3 grid, "
+            "all 100k points of a synthetic PCPNet-shape cloud per GPU per step")
+
+
+def config(n_gpus):
+    return {"workload": WORKLOAD, "cloud_points": N_POINTS, "queries_per_gpu_per_step": N_POINTS,
+            "clouds_per_step": n_gpus, "scales": RADIUS, "points_per_patch": P, "grid": "%dx%dx%d" % (RES, RES, RES),
+            "gmm_variance": VARIANCE, "seed": SEED,
+            "partitioning": "query points sharded across %d GPU(s), cloud replicated, per-rank slabs, no collective" % n_gpus,
+            "l2": "each step writes 16.4 GB of MuPS + 2.5 GB of patches per GPU (>> 126 MB L2) and cycles "
+                  "through %d clouds; no explicit flush needed" % N_CLOUDS}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm (the only places bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_pass(pts, kdtree, query_idx, gmm_feed):
+    """One bounded pass of the reference's CPU path: cKDTree ball queries on all cores (the
+    reference's own dependency and predicate), the shared seeded selection, gather/centre/normalise
+    (oracle restatement of pcpnet_dataset.py:286-343) and the OpenMP C port of get_3dmfv_n_est +
+    MuPS assembly.  Returns the number of query points."""
+    from oracle import c_oracle
+    from oracle import mups_oracle as orc
+    w, mu, sigma = gmm_feed
+    rads = orc.absolute_radii(pts, RADIUS)
+    S = len(rads)
+    B = len(query_idx)
+    patches = np.zeros((B, S * P, 3), np.float32)
+    n_eff = np.zeros((B, S), np.int32)
+    centres = pts[query_idx]
+    for s, rad in enumerate(rads):
+        lists = kdtree.query_ball_point(centres, rad, workers=-1)
+        for b, inds in enumerate(lists):
+            inds = np.asarray(inds, np.int64)
+            n_eff[b, s] = min(P, len(inds))
+            inds = orc.select_subset(inds, P, SEED, int(query_idx[b]), s)
+            patches[b, s * P: s * P + len(inds)] = (pts[inds] - centres[b]) / np.float32(rad)
+    c_oracle.mups(patches, n_eff, w, mu, sigma, S)
+    return B
+
+
+def cpu_sample_queries(step, n):
+    return (np.arange(n, dtype=np.int64) * (N_POINTS // n) + step) % N_POINTS
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    from oracle import mups_oracle as orc
+    c_oracle.build()
+    sample = 512
+    clouds = [orc.synthetic_cloud(N_POINTS, cloud_id=i) for i in range(N_CLOUDS)]
+    trees = [orc.build_kdtree(p) for p in clouds]
+    feed = orc.gmm_feed(*orc.get_3d_grid_gmm([RES] * 3, VARIANCE))
+    for i in range(args.warmup):
+        cpu_reference_pass(clouds[i % N_CLOUDS], trees[i % N_CLOUDS], cpu_sample_queries(i, sample), feed)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(args.steps):
+        done += cpu_reference_pass(clouds[i % N_CLOUDS], trees[i % N_CLOUDS], cpu_sample_queries(i, sample), feed)
+    dt = time.perf_counter() - t0
+    value = done / dt
+    cores = os.cpu_count()
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config(args.gpus),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "threads_half2": c_oracle.num_threads(),
+                            "kind": "port",
+                            "sample": "%d strided query points of the 100k per step (kd-tree build excluded); "
+                                      "cKDTree.query_ball_point(workers=-1) + oracle C port (OpenMP) of get_3dmfv_n_est" % sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+
+def fp32_micro_peak():
+    """Measured FP32 FMA-pipe issue rate (T op-slots/s) from profiles/microbench, else None."""
+    exe = os.path.join(ROOT, "profiles", "microbench")
+    if not os.path.exists(exe):
+        return None, None
+    try:
+        txt = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None, None
+    ffma, mufu = [], []
+    for line in txt.splitlines():
+        try:
+            d = json.loads(line)
+        except ValueError:
+            continue
+        if d.get("test") == "ffma":
+            ffma.append(d["glane_op_per_s"] / 1e3)
+        if d.get("test") == "mufu_ex2":
+            mufu.append(d["glane_op_per_s"] / 1e3)
+    return (max(ffma) if ffma else None), (max(mufu) if mufu else None)
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    import nesti_net_b200 as mb
+    from nesti_net_b200 import _lib
+    from oracle import mups_oracle as orc       # synthetic clouds + the cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the MuPS path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    _lib.load()
+
+    g = mb.get_3d_grid_gmm([RES] * 3, VARIANCE)
+    gmm = mb.gmm_handle(g.weights_, g.means_, np.sqrt(g.covariances_))
+    S, G = len(RADIUS), gmm.G
+    clouds_host = [orc.synthetic_cloud(N_POINTS, cloud_id=i) for i in range(max(N_CLOUDS, n_gpus))]
+    clouds_dev = [torch.from_numpy(c).to(dev) for c in clouds_host]
+    bounds = mb.dist.shard_bounds(N_POINTS, n_gpus)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    q_shard = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+    per_cloud = hi - lo
+    rows = per_cloud * n_gpus                                   # query points this rank computes per step
+    feats = torch.empty((rows, RES, RES, RES, 20 * S), dtype=torch.float32, device=dev)
+    patches = torch.empty((rows, S * P, 3), dtype=torch.float32, device=dev)
+    n_eff = torch.empty((rows, S), dtype=torch.int32, device=dev)
+    total = torch.empty((rows, S), dtype=torch.int32, device=dev)
+    L = _lib.load()
+    import ctypes
+    stream = torch.cuda.current_stream(dev)
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+
+    stat_events = []
+
+    def step(i, timed):
+        """One pass of the hot path: n_gpus clouds, this rank's query shard of each."""
+        for c in range(n_gpus):
+            xyz = clouds_dev[(i * n_gpus + c) % len(clouds_dev)]
+            index = mb.PointIndex(xyz, cell_frac=max(RADIUS))
+            radii = np.ascontiguousarray(index.absolute_radii(RADIUS), dtype=np.float64)
+            sl = slice(c * per_cloud, (c + 1) * per_cloud)
+            _lib.check(L.mups_ball_query(index.handle, ctypes.c_void_p(q_shard.data_ptr()), per_cloud,
+                                         radii.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), S, P, SEED, None,
+                                         ctypes.c_void_p(total[sl].data_ptr()), ctypes.c_void_p(patches[sl].data_ptr()),
+                                         ctypes.c_void_p(n_eff[sl].data_ptr()), sptr))
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _lib.check(L.mups_3dmfv(gmm.handle, ctypes.c_void_p(patches[sl].data_ptr()), ctypes.c_void_p(n_eff[sl].data_ptr()),
+                                    per_cloud, S, P, _lib.FLAG_MASKED, ctypes.c_void_p(feats[sl].data_ptr()), sptr))
+            e1.record(stream)
+            if timed:
+                stat_events.append((e0, e1))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp32_peak_measured, mufu_peak_measured = (None, None)
+    if rank == 0:
+        fp32_peak_measured, mufu_peak_measured = fp32_micro_peak()
+
+    for i in range(args.warmup):
+        step(i, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i, True)
+    t1.record(stream)
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = rows * n_gpus * args.steps / (ms_total * 1e-3)
+
+    # the dominant kernel: statistics.  Algorithmic work of the last step's launches on this rank.
+    ne = n_eff.cpu().numpy()
+    m_unmasked = np.where(ne >= P - 1, P, ne + 1).astype(np.int64)
+    pairs_step = float(m_unmasked.sum()) * G
+    stat_ms = float(np.mean([a.elapsed_time(b) for a, b in stat_events])) * n_gpus      # per step (n_gpus launches)
+    stats_tflops = OPS_PER_PAIR * pairs_step / (stat_ms * 1e-3) / 1e12
+    sm_max_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fp32_peak_nominal = 148 * 128 * sm_max_mhz * 1e6 / 1e12        # T op-slots/s (FMA counted once)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    out_bytes_step = float(rows) * G * 20 * S * 4
+    roofline = {
+        "kernel": "stats_separable_kernel (K5, 3DmFV statistics)",
+        "bound": "fp32",
+        "achieved": stats_tflops, "peak": fp32_peak_nominal, "unit": "TFLOP/s", "frac": stats_tflops / fp32_peak_nominal,
+        "peak_is": "148 SMs x 128 FP32 lanes x %.0f MHz op-slots/s (FMA counted once, SURVEY.md 8d); MEASURED_PEAKS.json "
+                   "holds only HBM/bf16 peaks" % sm_max_mhz,
+        "peak_measured_ffma": fp32_peak_measured, "peak_measured_mufu_ex2": mufu_peak_measured,
+        "algorithmic_ops_per_pair": OPS_PER_PAIR, "pairs_per_launch": pairs_step / n_gpus,
+        "pairs_per_query": pairs_step / rows, "kernel_ms_per_launch": stat_ms / n_gpus,
+        "kernel_share_of_step": stat_ms / (ms_total / args.steps),
+        "mufu_exp_per_s_algorithmic": pairs_step / (stat_ms * 1e-3),
+        "hbm": {"achieved": out_bytes_step / (stat_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": out_bytes_step / (stat_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_is": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"},
+        "traffic": None,
+    }
+    prof = os.path.join(ROOT, "profiles", "stats_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            t = json.load(open(prof))
+            roofline["traffic"] = t["dram_bytes_per_query"] * rows / n_gpus
+            roofline["traffic_source"] = t.get("source")
+        except Exception:
+            pass
+
+    # ---- end to end through the public API with host buffers ------------------------------------------
+    pipe = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=8192)
+    hosts = [torch.from_numpy(c).pin_memory() for c in clouds_host]
+    q_host = torch.arange(lo, hi, dtype=torch.int64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step(i):
+        n = 0
+        for c in range(n_gpus):
+            n += pipe.features_to_host(hosts[(i * n_gpus + c) % len(hosts)], q_host)
+        return n
+
+    e2e_step(0)
+    barrier()
+    pipe.h2d_bytes = pipe.d2h_bytes = 0
+    w0 = time.perf_counter()
+    n_done = 0
+    for i in range(e2e_steps):
+        n_done += e2e_step(1 + i)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    barrier()
+    e2e = {"value": n_done * n_gpus / float(e2e_s.item()), "unit": UNIT, "steps": e2e_steps,
+           "h2d_bytes_per_step": pipe.h2d_bytes // e2e_steps, "d2h_bytes_per_step": pipe.d2h_bytes // e2e_steps,
+           "api": "MuPSPipeline.features_to_host (pinned host cloud in, MuPS rows streamed to pinned host memory)"}
+
+    if rank == 0:
+        # ---- CPU baseline on a bounded sample (the oracle is the thing timed here, never the product) ----
+        from oracle import c_oracle
+        c_oracle.build()
+        feed = orc.gmm_feed(*orc.get_3d_grid_gmm([RES] * 3, VARIANCE))
+        tree = orc.build_kdtree(clouds_host[0])
+        sample = 1024
+        cpu_reference_pass(clouds_host[0], tree, cpu_sample_queries(0, 64), feed)
+        c0 = time.perf_counter()
+        done = cpu_reference_pass(clouds_host[0], tree, cpu_sample_queries(1, sample), feed)
+        cdt = time.perf_counter() - c0
+        cpu_baseline = {"value": done / cdt, "unit": UNIT, "cores": os.cpu_count(), "threads_half2": c_oracle.num_threads(),
+                        "kind": "port",
+                        "sample": "%d strided query points of cloud 0 (kd-tree build excluded); cKDTree.query_ball_point("
+                                  "workers=-1) + oracle C port (OpenMP) of get_3dmfv_n_est" % sample}
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": config(n_gpus), "roofline": roofline,
+               "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -337,11 +337,14 @@ __device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 
 // A thread fetches both points' factors as packed f32x2 operands with one LDS.128 + one LDS.64 per
 // axis entry; consecutive lattice indices are consecutive 16 B / 8 B words, so a warp's loads
 // (<= 8 distinct j, <= 4 distinct i, one k-quad) are bank-conflict free.
-template <int MINB, bool PACKED_SUMS>
+// LOG_RES: the lattice is RES x RES x RES with RES = 1 << LOG_RES in {4, 8, 16, 32} (get_3d_grid_gmm is always
+// called with [n, n, n]); other lattices take the general kernel.
+template <int MINB, bool PACKED_SUMS, int LOG_RES>
 __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(const StatsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = kSepThreads, TPP = kSepTilePoints / 2;
-    const int nx = a.res[0], ny = a.res[1], nz = a.res[2];
+    constexpr int RES = 1 << LOG_RES;
+    constexpr int nx = RES, ny = RES, nz = RES;
     float4* FA[3];
     float2* FB[3];
     FA[0] = reinterpret_cast<float4*>(smem_raw);
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
     float* lat = reinterpret_cast<float*>(FB[2] + TPP * nz);   // [3][64] lattice coordinates
     float* red = lat + 3 * 64;                                 // [NT/32][20]
     float* inv_norm = red + (NT / 32) * 20;                    // [20] (+12 pad)
+    float* axis_par = inv_norm + 20;                           // [3][4]: 1/sigma, guard lo, guard hi
     float* coords = inv_norm + 32;                             // [3*P] the patch, staged once (coalesced)
     __shared__ int s_fallback;
 
@@ -370,6 +374,7 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
 
     for (int i = tid; i < 3 * 64; i += NT) lat[i] = __ldg(a.axis_mu + i);
     for (int i = tid; i < 3 * m; i += NT) coords[i] = __ldg(src + i);
+    if (tid < 3) { axis_par[4 * tid] = a.isig[tid]; axis_par[4 * tid + 1] = a.guard_lo[tid]; axis_par[4 * tid + 2] = a.guard_hi[tid]; }
     if (tid == 0) s_fallback = 0;
 
     const float w = a.w_uniform;
@@ -378,10 +383,10 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
     const float inv_npts = masked ? 1.0f / (float)n_eff : 1.0f;         // tf_util.py:722-730
     const float pis = rsw * inv_static, smu = rsw * inv_static, ssg = rs2w * inv_static;
 
-    const int nzq = nz / kSepKPT;
-    const int nxy = nx * ny;
-    const int tasks = nxy * nzq;
-    const int groups = (tasks + NT - 1) / NT;
+    constexpr int nzq = nz / kSepKPT;
+    constexpr int nxy = nx * ny;
+    constexpr int tasks = nxy * nzq;
+    constexpr int groups = (tasks + NT - 1) / NT;
     float sq[20];
 #pragma unroll
     for (int c = 0; c < 20; ++c) sq[c] = 0.f;
@@ -410,33 +415,41 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
         for (int tile0 = 0; tile0 < m; tile0 += kSepTilePoints) {
             const int tile_pts = min(kSepTilePoints, m - tile0);
             const int npairs = (tile_pts + 1) >> 1;
-            // ---- stage the per-axis factors of this tile: one lane per (point, lattice index) ------------
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax) {
-                const int na = a.res[ax], sh = a.shift[ax];
-                const float isg = a.isig[ax], glo = a.guard_lo[ax], ghi = a.guard_hi[ax];
-                const int total = (2 * npairs) << sh;
+            // ---- stage the per-axis factors of this tile: one lane per (point pair, axis, lattice index) ----
+            {
+                const int total = (npairs * 3) << LOG_RES;
+                const float* ctile = coords + 3 * tile0;
+                const int last = tile_pts - 1;                                     // last real point of the tile
+                bool bad = false;
                 for (int base = 0; base < total; base += NT) {
                     const int idx = base + tid;
-                    const int li = idx & (na - 1);
-                    const int nl = idx >> sh;
-                    const int n = tile0 + nl;
-                    const bool real = n < m;                                // false for the odd tail and idle lanes
-                    const float c = coords[3 * (real ? n : 0) + ax];
-                    const float t = (c - lat[ax * 64 + li]) * isg;
-                    const float e = ex2_approx(kNegHalfLog2e * t * t);
-                    float sum = e;
-                    for (int o = na >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                    if (idx < total) {
-                        const float q = real ? e * __frcp_rn(sum) : 0.f;    // a missing second point contributes exact zeros
-                        const float qa = q * t;
-                        float* fa = reinterpret_cast<float*>(FA[ax] + ((nl >> 1) << sh) + li);
-                        fa[nl & 1] = q;
-                        fa[2 + (nl & 1)] = qa;
-                        reinterpret_cast<float*>(FB[ax] + ((nl >> 1) << sh) + li)[nl & 1] = fmaf(qa, t, -q);
-                        if (real && !(c >= glo && c <= ghi)) s_fallback = 1;   // outside the 5-sigma box (or NaN)
+                    const int li = idx & (RES - 1);
+                    const int r = min(idx, total - 1) >> LOG_RES;                   // r = 3 * pair + axis (idle lanes clamp)
+                    const int pp = r / 3, ax = r - 3 * pp;
+                    const bool real1 = 2 * pp + 1 <= last;                          // the odd tail has no second point
+                    const float c0 = ctile[6 * pp + ax];
+                    const float c1 = ctile[3 * min(2 * pp + 1, last) + ax];
+                    const float mu_l = lat[ax * 64 + li], isg = axis_par[4 * ax];
+                    const float t0 = (c0 - mu_l) * isg, t1 = (c1 - mu_l) * isg;
+                    const float e0 = ex2_approx(kNegHalfLog2e * t0 * t0), e1 = ex2_approx(kNegHalfLog2e * t1 * t1);
+                    float s0 = e0, s1 = e1;
+#pragma unroll
+                    for (int o = RES >> 1; o > 0; o >>= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     }
+                    const float q0 = __fdividef(e0, s0);
+                    const float q1 = real1 ? __fdividef(e1, s1) : 0.f;              // a missing second point contributes exact zeros
+                    const float a0 = q0 * t0, a1 = q1 * t1;
+                    if (idx < total) {
+                        const int slot = ax * (TPP * RES) + (pp << LOG_RES) + li;   // FA[ax] / FB[ax] are contiguous
+                        FA[0][slot] = make_float4(q0, q1, a0, a1);
+                        FB[0][slot] = make_float2(fmaf(a0, t0, -q0), fmaf(a1, t1, -q1));
+                    }
+                    const float glo = axis_par[4 * ax + 1], ghi = axis_par[4 * ax + 2];
+                    bad |= !(c0 >= glo && c0 <= ghi) || !(c1 >= glo && c1 <= ghi);   // outside the 5-sigma box (or NaN)
                 }
+                if (bad) s_fallback = 1;
             }
             __syncthreads();
             if (s_fallback) break;
@@ -597,7 +610,7 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
     }
     // the lattice fast path: power-of-two axes (shuffle reductions), 4 | nz, even P (points are consumed in pairs)
     const bool fast = gmm->separable && !(flags & MUPS_FLAG_NO_FASTPATH) && work != nullptr && (P % 2 == 0) &&
-                      pow2_in(gmm->res[0], 4, 32) && pow2_in(gmm->res[1], 4, 32) && pow2_in(gmm->res[2], 4, 32);
+                      pow2_in(gmm->res[0], 4, 32) && gmm->res[1] == gmm->res[0] && gmm->res[2] == gmm->res[0];
     if (!fast) return dispatch_general(a, items, (int)items, st);
 
     a.work_count = work;
@@ -607,16 +620,24 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
     const size_t smem = (size_t)TPP * (a.res[0] + a.res[1] + a.res[2]) * (sizeof(float4) + sizeof(float2)) +
                         sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
     const int variant = g_stats_variant.load();
-#define MUPS_LAUNCH_SEP(MINB, PACKED)                                                                               \
+#define MUPS_LAUNCH_SEP(MINB, PACKED, LOG)                                                                          \
     do {                                                                                                            \
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, PACKED>,                                    \
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, PACKED, LOG>,                               \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-        stats_separable_kernel<MINB, PACKED><<<(unsigned)items, kSepThreads, smem, st>>>(a);                        \
+        stats_separable_kernel<MINB, PACKED, LOG><<<(unsigned)items, kSepThreads, smem, st>>>(a);                   \
     } while (0)
-    if (variant == 2) MUPS_LAUNCH_SEP(2, true);
-    else if (variant == 3) MUPS_LAUNCH_SEP(3, true);
-    else if (variant == 5) MUPS_LAUNCH_SEP(3, false);
-    else MUPS_LAUNCH_SEP(4, false);
+#define MUPS_LAUNCH_SEP_RES(MINB, PACKED)                                                                           \
+    do {                                                                                                            \
+        if (a.shift[0] == 2) MUPS_LAUNCH_SEP(MINB, PACKED, 2);                                                      \
+        else if (a.shift[0] == 3) MUPS_LAUNCH_SEP(MINB, PACKED, 3);                                                 \
+        else if (a.shift[0] == 4) MUPS_LAUNCH_SEP(MINB, PACKED, 4);                                                 \
+        else MUPS_LAUNCH_SEP(MINB, PACKED, 5);                                                                      \
+    } while (0)
+    if (variant == 2) MUPS_LAUNCH_SEP_RES(2, true);
+    else if (variant == 3) MUPS_LAUNCH_SEP_RES(3, true);
+    else if (variant == 5) MUPS_LAUNCH_SEP_RES(3, false);
+    else MUPS_LAUNCH_SEP_RES(4, false);
+#undef MUPS_LAUNCH_SEP_RES
 #undef MUPS_LAUNCH_SEP
     MUPS_CHECK_LAUNCH();
     // patches that left the lattice's 5-sigma box (none for real patches, which live in the unit ball)
