@@ -64,47 +64,93 @@ def config(n_gpus):
 # ------------------------------------------------------------------------------------------------
 
 class ClockSampler(object):
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled through NVML (what nvidia-smi reads) every 50 ms
+    from a background thread.  NVML is initialised in __init__, i.e. before the warm-up steps, so
+    that no driver start-up cost lands in the timed region; samples are kept only between
+    start() and stop().  Falls back to an `nvidia-smi -lms` child process when pynvml is missing."""
+    SMI_FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.samples = []
+        self.samples = []          # (sm_mhz, max_mhz, power_w, reasons set)
+        self.recording = False
+        self.alive = True
+        self.nvml = None
         self.proc = None
-        self.gpu_index = gpu_index
-
-    def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: NVML enumerates physical GPUs
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            threading.Thread(target=self._poll_nvml, daemon=True).start()
         except Exception:
-            self.proc = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.SMI_FIELDS,
+                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                threading.Thread(target=self._poll_smi, daemon=True).start()
+            except Exception:
+                self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+    def _poll_nvml(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while self.alive:
+            if self.recording:
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                    pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                    mask = int(get_reasons(self.handle))
+                    self.samples.append((sm, self.max_mhz, pw, {k for k, b in bits.items() if mask & b}))
+                except Exception:
+                    pass
+            time.sleep(0.05)
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons, power = [], [], set(), []
+    def _poll_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 7:
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if not self.recording or len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+                self.samples.append((float(f[0]), float(f[1]), float(f[2]),
+                                     {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
             except ValueError:
-                continue
-            for name, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                pass
+
+    def start(self):
+        self.samples = []
+        self.recording = True
+
+    def stop(self):
+        self.recording = False
+        self.alive = False
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = [x[0] for x in self.samples]
+        reasons = set()
+        for x in self.samples:
+            reasons |= x[3]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(x[1] for x in self.samples) if sm else None,
+                "power_w_max": max(x[2] for x in self.samples) if sm else None, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -267,10 +313,10 @@ def run_own(args):
     if rank == 0:
         fp32_peak_measured, mufu_peak_measured = fp32_micro_peak()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # NVML comes up before the warm-up, not inside the timed region
     for i in range(args.warmup):
         step(i, False)
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()

@@ -5,9 +5,15 @@
 //   gather / centre / /rad (:330-343) -> IEEE fp32 subtract and true division
 //
 // One CTA per centre point; all S radii are classified in the same scan of the candidate cells.
-// Pass A counts neighbours per radius and histograms the selection keys' top bits, the radix
-// threshold of every over-full radius is found in shared memory, pass B collects the selected
-// neighbours, which are then sorted by point index and written as normalised patches.
+//   scan     the points of the (2R+1)^3 candidate cells are one flat range list, strided by the
+//            whole CTA (coalesced float4 loads, balanced); neighbours are counted per radius and
+//            appended to a shared-memory hit list (position + radius mask)
+//   select   only for radii with more than P neighbours: philox keys of the listed hits (dense, no
+//            divergence) -> 10-bit radix histogram -> threshold bin -> everything below is taken,
+//            the threshold group is resolved by rank counting (deeper radix levels if it is large)
+//   order    the <= P selected neighbours of each radius are bucket-sorted by point index
+//   K4       gather, centre on the query point, divide by float32(r), zero padding
+// A ball with more neighbours than the hit list holds (dense scans) re-scans instead of listing.
 #include "mups_common.cuh"
 
 namespace mups {
@@ -15,7 +21,9 @@ namespace mups {
 constexpr int kQT = 256;            // threads per query CTA
 constexpr int kBinBits = 10;
 constexpr int kBins = 1 << kBinBits;
-constexpr int kBoundaryCap = 512;   // max entries of the threshold radix group resolved by rank counting
+constexpr int kBoundaryCap = 256;   // max entries of the threshold radix group resolved by rank counting
+constexpr int kHitCap = 4096;       // neighbours (any radius) kept in the shared-memory hit list
+constexpr int kRangeCap = 64;       // candidate cells per scan batch
 
 struct QueryArgs {
     const float4* sorted;
@@ -47,6 +55,11 @@ struct QueryCtx {
     uint32_t center;
 };
 
+struct ScanTables {
+    uint32_t start[kRangeCap];
+    uint32_t prefix[kRangeCap + 1];
+};
+
 // cKDTree leaf predicate: s = 0; s += d*d for x, y, z in float64 without FMA contraction; s <= r*r
 // (scipy/spatial/ckdtree/src/distance_base.h sqeuclidean_distance_double, m = 3).
 __device__ __forceinline__ bool inside_exact(const QueryCtx& c, const float4& p, double r2) {
@@ -58,23 +71,53 @@ __device__ __forceinline__ bool inside_exact(const QueryCtx& c, const float4& p,
 }
 
 // Visits every neighbour of the centre (any radius): f(position in sorted, original index, bitmask of radii).
+// Block-wide: contains __syncthreads(); every thread of the CTA must call it.
 template <class F>
-__device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx& c, F&& f) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = kQT >> 5;
+__device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx& c, ScanTables& st, F&& f) {
+    const int tid = threadIdx.x, lane = tid & 31;
     const int nx = c.x1 - c.x0 + 1, ny = c.y1 - c.y0 + 1, nz = c.z1 - c.z0 + 1;
     const int ncell = nx * ny * nz;
     const float slack = 1e-3f * c.cell;
-    for (int ci = warp; ci < ncell; ci += nwarp) {
-        const int ix = c.x0 + ci % nx, iy = c.y0 + (ci / nx) % ny, iz = c.z0 + ci / (nx * ny);
-        // distance from the centre to the cell's box (shrunk by the rounding slack of the cell assignment)
-        const float lx = c.ox + ix * c.cell, ly = c.oy + iy * c.cell, lz = c.oz + iz * c.cell;
-        const float gx = fmaxf(0.f, fmaxf(lx - c.cx, c.cx - (lx + c.cell)) - slack);
-        const float gy = fmaxf(0.f, fmaxf(ly - c.cy, c.cy - (ly + c.cell)) - slack);
-        const float gz = fmaxf(0.f, fmaxf(lz - c.cz, c.cz - (lz + c.cell)) - slack);
-        if (gx * gx + gy * gy + gz * gz > a.r2_hi_max) continue;
-        const uint32_t code = morton3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
-        const uint32_t st = __ldg(a.cell_start + code), en = __ldg(a.cell_start + code + 1);
-        for (uint32_t i = st + lane; i < en; i += 32) {
+    for (int cbase = 0; cbase < ncell; cbase += kRangeCap) {
+        if (tid < 32) {   // warp 0 builds the range table of this batch: two cells per lane
+            uint32_t cnt[2], beg[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ci = cbase + 2 * lane + h;
+                cnt[h] = 0u; beg[h] = 0u;
+                if (ci < ncell) {
+                    const int ix = c.x0 + ci % nx, iy = c.y0 + (ci / nx) % ny, iz = c.z0 + ci / (nx * ny);
+                    // distance from the centre to the cell's box (shrunk by the rounding slack of the cell assignment)
+                    const float lx = c.ox + ix * c.cell, ly = c.oy + iy * c.cell, lz = c.oz + iz * c.cell;
+                    const float gx = fmaxf(0.f, fmaxf(lx - c.cx, c.cx - (lx + c.cell)) - slack);
+                    const float gy = fmaxf(0.f, fmaxf(ly - c.cy, c.cy - (ly + c.cell)) - slack);
+                    const float gz = fmaxf(0.f, fmaxf(lz - c.cz, c.cz - (lz + c.cell)) - slack);
+                    if (gx * gx + gy * gy + gz * gz <= a.r2_hi_max) {
+                        const uint32_t code = morton3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+                        beg[h] = __ldg(a.cell_start + code);
+                        cnt[h] = __ldg(a.cell_start + code + 1) - beg[h];
+                    }
+                }
+            }
+            uint32_t inc = cnt[0] + cnt[1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const uint32_t exc = inc - cnt[0] - cnt[1];
+            st.start[2 * lane] = beg[0];
+            st.start[2 * lane + 1] = beg[1];
+            st.prefix[2 * lane] = exc;
+            st.prefix[2 * lane + 1] = exc + cnt[0];
+            if (lane == 31) st.prefix[kRangeCap] = inc;
+        }
+        __syncthreads();
+        const uint32_t total = st.prefix[kRangeCap];
+        int k = 0;
+        for (uint32_t fi = tid; fi < total; fi += kQT) {
+            while (fi >= st.prefix[k + 1]) ++k;
+            const uint32_t i = st.start[k] + (fi - st.prefix[k]);
             const float4 p = __ldg(a.sorted + i);
             const float dx = p.x - c.cx, dy = p.y - c.cy, dz = p.z - c.cz;
             const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
@@ -88,6 +131,7 @@ __device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx&
             }
             if (in) f(i, (uint32_t)__float_as_int(p.w), in);
         }
+        __syncthreads();
     }
 }
 
@@ -139,26 +183,58 @@ __device__ __forceinline__ void warp_find_threshold(const uint32_t* hist, int nb
     *group = __shfl_sync(0xffffffffu, t_group, src);
 }
 
+// Exclusive scan of kBins counters by the whole CTA (kBins / kQT per thread), in place.
+__device__ __forceinline__ void block_scan_bins(uint32_t* bins, uint32_t* warp_sums /*[kQT/32]*/) {
+    constexpr int PER = kBins / kQT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t v[PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { v[k] = bins[tid * PER + k]; s += v[k]; }
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; ++w) off += warp_sums[w];
+    uint32_t run = off + inc - s;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { bins[tid * PER + k] = run; run += v[k]; }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = a.S, P = a.P, Ppad = a.Ppad;
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);                                  // [S][kBins]
-    unsigned long long* sel = reinterpret_cast<unsigned long long*>(hist + a.S * kBins);     // [S][Ppad]  (idx << 32 | pos)
-    unsigned long long* bnd = sel + (size_t)a.S * a.Ppad;                                    // [S][kBoundaryCap] (key << 32 | hit slot)
-    uint32_t* bnd_pos = reinterpret_cast<uint32_t*>(bnd + (size_t)a.S * kBoundaryCap);       // [S][kBoundaryCap] position in sorted
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(hist + S * kBins);       // [S][Ppad]  (idx << 32 | pos)
+    unsigned long long* bnd = sel + (size_t)S * Ppad;                                        // [S][kBoundaryCap] (key << 32 | idx)
+    uint32_t* bnd_pos = reinterpret_cast<uint32_t*>(bnd + (size_t)S * kBoundaryCap);         // [S][kBoundaryCap] position in sorted
+    // the hit list (scan .. select) and the sort's second buffer (order) share one region
+    unsigned char* shared_region = reinterpret_cast<unsigned char*>(bnd_pos + (size_t)S * kBoundaryCap);
+    uint32_t* hit_pos = reinterpret_cast<uint32_t*>(shared_region);                           // [kHitCap]
+    unsigned char* hit_mask = reinterpret_cast<unsigned char*>(hit_pos + kHitCap);            // [kHitCap]
+    unsigned long long* tmp = reinterpret_cast<unsigned long long*>(shared_region);           // [S][Ppad]
+    __shared__ ScanTables st;
     __shared__ uint32_t s_cnt[MUPS_MAX_SCALES], s_nsel[MUPS_MAX_SCALES], s_nb[MUPS_MAX_SCALES];
     __shared__ uint32_t s_prefix[MUPS_MAX_SCALES], s_bits[MUPS_MAX_SCALES], s_need[MUPS_MAX_SCALES];
-    __shared__ uint32_t s_unresolved;
+    __shared__ uint32_t s_min[MUPS_MAX_SCALES], s_max[MUPS_MAX_SCALES];
+    __shared__ uint32_t s_unresolved, s_nhits;
+    __shared__ uint32_t s_warp_sums[kQT / 32];
 
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = a.S, P = a.P;
     const int64_t q = a.q[b];
 
     for (int i = tid; i < S * kBins; i += kQT) hist[i] = 0u;
     if (tid < MUPS_MAX_SCALES) {
         s_cnt[tid] = 0u; s_nsel[tid] = 0u; s_nb[tid] = 0u; s_prefix[tid] = 0u; s_bits[tid] = 0u; s_need[tid] = 0u;
+        s_min[tid] = 0xFFFFFFFFu; s_max[tid] = 0u;
     }
-    if (tid == 0) s_unresolved = 0u;
+    if (tid == 0) { s_unresolved = 0u; s_nhits = 0u; }
 
     if (q < 0 || q >= a.n) {   // invalid centre: empty patch, total = -1
         for (int i = tid; i < S * P; i += kQT) {
@@ -188,21 +264,16 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
     }
     __syncthreads();
 
-    // ---- pass A: neighbour count per radius + first-level key histogram -------------------------
+    // ---- scan: neighbour count per radius + hit list ---------------------------------------------
     {
         uint32_t cnt[MUPS_MAX_SCALES];
 #pragma unroll
         for (int s = 0; s < MUPS_MAX_SCALES; ++s) cnt[s] = 0u;
-        for_each_hit(a, c, [&](uint32_t, uint32_t idx, uint32_t in) {
-            uint32_t key[MUPS_MAX_SCALES];
-            selection_keys(a, c.center, idx, in, key);
+        for_each_hit(a, c, st, [&](uint32_t pos, uint32_t, uint32_t in) {
 #pragma unroll
-            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
-                if (in & (1u << s)) {
-                    ++cnt[s];
-                    atomicAdd(hist + s * kBins + (key[s] >> (32 - kBinBits)), 1u);
-                }
-            }
+            for (int s = 0; s < MUPS_MAX_SCALES; ++s) cnt[s] += (in >> s) & 1u;
+            const uint32_t slot = atomicAdd(&s_nhits, 1u);
+            if (slot < (uint32_t)kHitCap) { hit_pos[slot] = pos; hit_mask[slot] = (unsigned char)in; }
         });
 #pragma unroll
         for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
@@ -215,87 +286,111 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
         }
     }
     __syncthreads();
+    const uint32_t nhits = s_nhits;
+    const bool listed = nhits <= (uint32_t)kHitCap;     // else: every pass re-scans the cells
+    uint32_t over = 0;                                   // radii with more than P neighbours need keys
+    for (int s = 0; s < S; ++s) over |= (s_cnt[s] > (uint32_t)P) ? (1u << s) : 0u;
 
-    // ---- radix threshold of the over-full radii (warp s handles radius s) -------------------------
-    if (warp < S && s_cnt[warp] > (uint32_t)P) {
-        uint32_t T, below, group;
-        warp_find_threshold(hist + warp * kBins, kBins, (uint32_t)P, lane, &T, &below, &group);
-        if (lane == 0) {
-            s_prefix[warp] = T; s_bits[warp] = kBinBits; s_need[warp] = (uint32_t)P - below;
-            if (group > (uint32_t)a.cap) atomicOr(&s_unresolved, 1u << warp);
+    // visits the neighbours that belong to at least one radius of `want`
+    auto visit = [&](uint32_t want, auto&& f) {
+        if (listed) {
+            for (uint32_t h = tid; h < nhits; h += kQT) {
+                const uint32_t in = hit_mask[h];
+                if (in & want) {
+                    const uint32_t pos = hit_pos[h];
+                    f(pos, (uint32_t)__float_as_int(__ldg(&a.sorted[pos].w)), in);
+                }
+            }
+            __syncthreads();
+        } else {
+            for_each_hit(a, c, st, [&](uint32_t pos, uint32_t idx, uint32_t in) { if (in & want) f(pos, idx, in); });
         }
-    }
-    __syncthreads();
+    };
 
-    // ---- refinement levels (only when a threshold group exceeds kBoundaryCap: > ~500k neighbours) ----
-    while (s_unresolved) {
-        const uint32_t unresolved = s_unresolved;
-        __syncthreads();
-        for (int i = tid; i < S * kBins; i += kQT)
-            if (unresolved & (1u << (i / kBins))) hist[i] = 0u;
-        if (tid == 0) s_unresolved = 0u;
-        __syncthreads();
-        for_each_hit(a, c, [&](uint32_t, uint32_t idx, uint32_t in) {
-            in &= unresolved;
-            if (!in) return;
+    if (over) {
+        // ---- first-level key histogram of the over-full radii ------------------------------------------
+        visit(over, [&](uint32_t, uint32_t idx, uint32_t in) {
+            in &= over;
             uint32_t key[MUPS_MAX_SCALES];
             selection_keys(a, c.center, idx, in, key);
 #pragma unroll
-            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
-                if (in & (1u << s)) {
-                    const uint32_t bits = s_bits[s];
-                    const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
-                    if ((key[s] >> (32u - bits)) == s_prefix[s])
-                        atomicAdd(hist + s * kBins + ((key[s] >> (32u - bits - nb)) & ((1u << nb) - 1u)), 1u);
-                }
-            }
+            for (int s = 0; s < MUPS_MAX_SCALES; ++s)
+                if (in & (1u << s)) atomicAdd(hist + s * kBins + (key[s] >> (32 - kBinBits)), 1u);
         });
-        __syncthreads();
-        if (warp < S && (unresolved & (1u << warp))) {
-            const uint32_t bits = s_bits[warp];
-            const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
+        // ---- radix threshold (warp s handles radius s) ----------------------------------------------------
+        if (warp < S && (over & (1u << warp))) {
             uint32_t T, below, group;
-            warp_find_threshold(hist + warp * kBins, 1 << nb, s_need[warp], lane, &T, &below, &group);
+            warp_find_threshold(hist + warp * kBins, kBins, (uint32_t)P, lane, &T, &below, &group);
             if (lane == 0) {
-                s_prefix[warp] = (s_prefix[warp] << nb) | T; s_bits[warp] = bits + nb; s_need[warp] -= below;
-                // with all 32 key bits fixed the group is a set of exact key ties; more than
-                // kBoundaryCap of them cannot be told apart here (never seen: needs >500 equal 32-bit keys)
-                if (group > (uint32_t)a.cap && bits + nb < 32u) atomicOr(&s_unresolved, 1u << warp);
+                s_prefix[warp] = T; s_bits[warp] = kBinBits; s_need[warp] = (uint32_t)P - below;
+                if (group > (uint32_t)a.cap) atomicOr(&s_unresolved, 1u << warp);
             }
         }
         __syncthreads();
-    }
-
-    // ---- pass B: collect the selection -----------------------------------------------------------------
-    {
-        uint32_t over = 0;   // radii that need keys
-        for (int s = 0; s < S; ++s) over |= (s_cnt[s] > (uint32_t)P) ? (1u << s) : 0u;
-        for_each_hit(a, c, [&](uint32_t pos, uint32_t idx, uint32_t in) {
-            uint32_t key[MUPS_MAX_SCALES];
-            selection_keys(a, c.center, idx, in & over, key);
+        // ---- refinement levels (only when a threshold group exceeds the cap: > ~250k neighbours) ----------
+        while (s_unresolved) {
+            const uint32_t unresolved = s_unresolved;
+            __syncthreads();
+            for (int i = tid; i < S * kBins; i += kQT)
+                if (unresolved & (1u << (i / kBins))) hist[i] = 0u;
+            if (tid == 0) s_unresolved = 0u;
+            __syncthreads();
+            visit(unresolved, [&](uint32_t, uint32_t idx, uint32_t in) {
+                in &= unresolved;
+                uint32_t key[MUPS_MAX_SCALES];
+                selection_keys(a, c.center, idx, in, key);
 #pragma unroll
-            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
-                if (!(in & (1u << s))) continue;
-                bool take = true;
-                if (over & (1u << s)) {
-                    const uint32_t hp = key[s] >> (32u - s_bits[s]);
-                    take = hp < s_prefix[s];
-                    if (hp == s_prefix[s]) {
-                        const uint32_t slot = atomicAdd(s_nb + s, 1u);
-                        if (slot < (uint32_t)kBoundaryCap) {
-                            bnd[s * kBoundaryCap + slot] = ((unsigned long long)key[s] << 32) | idx;
-                            bnd_pos[s * kBoundaryCap + slot] = pos;
-                        }
+                for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+                    if (in & (1u << s)) {
+                        const uint32_t bits = s_bits[s];
+                        const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
+                        if ((key[s] >> (32u - bits)) == s_prefix[s])
+                            atomicAdd(hist + s * kBins + ((key[s] >> (32u - bits - nb)) & ((1u << nb) - 1u)), 1u);
                     }
                 }
-                if (take) {
-                    const uint32_t slot = atomicAdd(s_nsel + s, 1u);
-                    if (slot < (uint32_t)a.Ppad) sel[(size_t)s * a.Ppad + slot] = ((unsigned long long)idx << 32) | pos;
+            });
+            if (warp < S && (unresolved & (1u << warp))) {
+                const uint32_t bits = s_bits[warp];
+                const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
+                uint32_t T, below, group;
+                warp_find_threshold(hist + warp * kBins, 1 << nb, s_need[warp], lane, &T, &below, &group);
+                if (lane == 0) {
+                    s_prefix[warp] = (s_prefix[warp] << nb) | T; s_bits[warp] = bits + nb; s_need[warp] -= below;
+                    // with all 32 key bits fixed the group is a set of exact key ties; more than the cap of
+                    // them cannot be told apart here (needs > 256 equal 32-bit keys in one ball)
+                    if (group > (uint32_t)a.cap && bits + nb < 32u) atomicOr(&s_unresolved, 1u << warp);
                 }
             }
-        });
+            __syncthreads();
+        }
     }
-    __syncthreads();
+
+    // ---- collect the selection ----------------------------------------------------------------------------
+    visit(0xFFu, [&](uint32_t pos, uint32_t idx, uint32_t in) {
+        uint32_t key[MUPS_MAX_SCALES];
+        selection_keys(a, c.center, idx, in & over, key);
+#pragma unroll
+        for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+            if (!(in & (1u << s))) continue;
+            bool take = true;
+            if (over & (1u << s)) {
+                const uint32_t hp = key[s] >> (32u - s_bits[s]);
+                take = hp < s_prefix[s];
+                if (hp == s_prefix[s]) {
+                    const uint32_t slot = atomicAdd(s_nb + s, 1u);
+                    if (slot < (uint32_t)kBoundaryCap) {
+                        bnd[s * kBoundaryCap + slot] = ((unsigned long long)key[s] << 32) | idx;
+                        bnd_pos[s * kBoundaryCap + slot] = pos;
+                    }
+                }
+            }
+            if (take) {
+                const uint32_t slot = atomicAdd(s_nsel + s, 1u);
+                if (slot < (uint32_t)Ppad) sel[(size_t)s * Ppad + slot] = ((unsigned long long)idx << 32) | pos;
+            }
+        }
+    });
+    if (!listed) __syncthreads();
 
     // ---- threshold group: keep the `need` smallest (key, index) pairs ------------------------------------
     for (int s = 0; s < S; ++s) {
@@ -307,36 +402,69 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
             for (uint32_t j = 0; j < m; ++j) rank += bnd[s * kBoundaryCap + j] < mine ? 1u : 0u;
             if (rank < need) {
                 const uint32_t slot = atomicAdd(s_nsel + s, 1u);
-                if (slot < (uint32_t)a.Ppad)
-                    sel[(size_t)s * a.Ppad + slot] = ((mine & 0xFFFFFFFFull) << 32) | bnd_pos[s * kBoundaryCap + i];
+                if (slot < (uint32_t)Ppad)
+                    sel[(size_t)s * Ppad + slot] = ((mine & 0xFFFFFFFFull) << 32) | bnd_pos[s * kBoundaryCap + i];
             }
         }
     }
     __syncthreads();
 
-    // ---- sort each radius' selection by point index (bitonic, shared memory), then K4 ----------------------
+    // ---- order every radius' selection by point index: bucket sort over the index range --------------------
+    // bucket(e) is monotone in the index, so bucket order + order inside a bucket = index order
+    for (int i = tid; i < S * kBins; i += kQT) hist[i] = 0u;
+    for (int s = 0; s < S; ++s) {
+        const uint32_t ne = min(s_cnt[s], (uint32_t)P);
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+        for (uint32_t t = tid; t < ne; t += kQT) {
+            const uint32_t id = (uint32_t)(sel[(size_t)s * Ppad + t] >> 32);
+            lo = min(lo, id); hi = max(hi, id);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0 && lo <= hi) { atomicMin(s_min + s, lo); atomicMax(s_max + s, hi); }
+    }
+    __syncthreads();
+    auto bucket_of = [&](int s, uint32_t id) {
+        const float scale = (float)kBins / ((float)(s_max[s] - s_min[s]) + 1.0f);
+        return min((uint32_t)(kBins - 1), (uint32_t)((float)(id - s_min[s]) * scale));
+    };
+    for (int s = 0; s < S; ++s) {
+        const uint32_t ne = min(s_cnt[s], (uint32_t)P);
+        for (uint32_t t = tid; t < ne; t += kQT)
+            atomicAdd(hist + s * kBins + bucket_of(s, (uint32_t)(sel[(size_t)s * Ppad + t] >> 32)), 1u);
+    }
+    __syncthreads();
+    for (int s = 0; s < S; ++s) block_scan_bins(hist + s * kBins, s_warp_sums);     // counts -> bucket starts
+    for (int s = 0; s < S; ++s) {
+        const uint32_t ne = min(s_cnt[s], (uint32_t)P);
+        for (uint32_t t = tid; t < ne; t += kQT) {
+            const unsigned long long e = sel[(size_t)s * Ppad + t];
+            const uint32_t slot = atomicAdd(hist + s * kBins + bucket_of(s, (uint32_t)(e >> 32)), 1u);   // starts -> ends
+            tmp[(size_t)s * Ppad + slot] = e;
+        }
+    }
+    __syncthreads();
+    for (int s = 0; s < S; ++s) {
+        const uint32_t ne = min(s_cnt[s], (uint32_t)P);
+        for (uint32_t t = tid; t < ne; t += kQT) {
+            const unsigned long long e = tmp[(size_t)s * Ppad + t];
+            const uint32_t bk = bucket_of(s, (uint32_t)(e >> 32));
+            const uint32_t beg = bk ? hist[s * kBins + bk - 1] : 0u, end = hist[s * kBins + bk];
+            uint32_t rank = 0;
+            for (uint32_t j = beg; j < end; ++j) rank += tmp[(size_t)s * Ppad + j] < e ? 1u : 0u;
+            sel[(size_t)s * Ppad + beg + rank] = e;
+        }
+    }
+    __syncthreads();
+
+    // ---- K4: gather, centre on the query point, divide by float32(r)  (pcpnet_dataset.py:330-343) ----------
     for (int s = 0; s < S; ++s) {
         const uint32_t total = s_cnt[s];
         const uint32_t ne = min(total, (uint32_t)P);
-        unsigned long long* v = sel + (size_t)s * a.Ppad;
-        uint32_t np2 = 1;
-        while (np2 < ne) np2 <<= 1;
-        for (uint32_t i = ne + tid; i < np2; i += kQT) v[i] = ~0ull;
-        __syncthreads();
-        for (uint32_t k = 2; k <= np2; k <<= 1) {
-            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                for (uint32_t i = tid; i < np2; i += kQT) {
-                    const uint32_t l = i ^ j;
-                    if (l > i) {
-                        const unsigned long long x = v[i], y = v[l];
-                        const bool up = (i & k) == 0;
-                        if ((x > y) == up) { v[i] = y; v[l] = x; }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        // K4: gather, centre on the query point, divide by float32(r)  (pcpnet_dataset.py:330-343)
+        const unsigned long long* v = sel + (size_t)s * Ppad;
         const float rf = a.rf[s];
         for (uint32_t t = tid; t < (uint32_t)P; t += kQT) {
             float ox = 0.f, oy = 0.f, oz = 0.f;
@@ -372,6 +500,7 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
     while (ppad < P) ppad <<= 1;
     a.Ppad = ppad;
     a.cap = g_boundary_cap.load();
+    if (a.cap > kBoundaryCap) a.cap = kBoundaryCap;
     double rmax = 0.0;
     float hi_max = 0.f;
     for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
@@ -387,16 +516,14 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
     a.r2_hi_max = hi_max;
     a.k0 = (uint32_t)(seed & 0xFFFFFFFFull); a.k1 = (uint32_t)(seed >> 32);
     a.nbr_idx = nbr_idx; a.nbr_total = nbr_total; a.patches = patches; a.n_eff = n_eff;
-    const size_t smem = (size_t)S * kBins * 4 + (size_t)S * ppad * 8 + (size_t)S * kBoundaryCap * 12;
+    const size_t region = (size_t)kHitCap * 5 > (size_t)S * ppad * 8 ? (size_t)kHitCap * 5 : (size_t)S * ppad * 8;
+    const size_t smem = (size_t)S * kBins * 4 + (size_t)S * ppad * 8 + (size_t)S * kBoundaryCap * 12 + region;
     if (smem > 200 * 1024) {
         set_error("ball query: S=%d, P=%d needs %zu bytes of shared memory", S, P, smem);
         return MUPS_ERR_UNSUPPORTED;
     }
-    static std::atomic<size_t> configured{0};
-    if (smem > 48 * 1024 && configured.load() < smem) {
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured.store(200 * 1024);
-    }
+    if (smem > 48 * 1024)
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (B > 0) {
         ball_query_kernel<<<(unsigned)B, kQT, smem, st>>>(a);
         MUPS_CHECK_LAUNCH();

@@ -128,6 +128,7 @@ def test_half1_against_reference_fixture(half1, case):
     (50000, 256, [0.07, 0.02, 0.05], "scan", 12345),                   # radii not ascending, non-uniform density
     (8000, 64, [0.02, 0.04, 0.06, 0.08, 0.1, 0.12, 0.14, 0.2], "pcpnet", (7 << 32) | 99),   # 8 scales, 64-bit seed
     (30000, 1024, [0.05, 0.1], "pcpnet", 1),
+    (40000, 128, [0.04, 0.35, 0.2], "pcpnet", 77),                      # > 4096 neighbours: the hit list overflows, re-scan path
 ])
 def test_half1_against_oracle(n, P, radius, kind, seed):
     pts = orc.synthetic_cloud(n, cloud_id=4, kind=kind, noise=0.002)
@@ -203,6 +204,15 @@ def test_half1_cell_size_independent_and_refinement_levels():
             _, _, out = run_half1(pts, q, radius, 128, cell_frac=0.1)
             for a, b in zip(out, ref):
                 assert np.array_equal(a, b), "boundary_cap=%d" % cap
+        # the same with balls too large for the shared-memory hit list (every pass re-scans the cells)
+        big = [0.05, 0.3]
+        ref_big = orc.gather_patches(pts, q[:24], big, 128, seed=SEED, return_indices=True)
+        assert ref_big[2].max() > 4096
+        for cap in (2, 256):
+            _lib.set_option("boundary_cap", cap)
+            _, _, out = run_half1(pts, q[:24], big, 128)
+            for a, b in zip(out, ref_big):
+                assert np.array_equal(a, b), "re-scan path, boundary_cap=%d" % cap
     finally:
         _lib.set_option("boundary_cap", 512)
     perm = np.random.RandomState(4).permutation(len(q))
