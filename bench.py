@@ -375,11 +375,14 @@ def run_own(args):
         except Exception:
             pass
 
+    skip = set(os.environ.get("MUPS_BENCH_SKIP", "").split(","))      # profiling runs only: "e2e,cpu"
     # ---- end to end through the public API with host buffers ------------------------------------------
-    pipe = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=8192)
+    pipe = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=8192 if "e2e" not in skip else 64)
     hosts = [torch.from_numpy(c).pin_memory() for c in clouds_host]
     q_host = torch.arange(lo, hi, dtype=torch.int64).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
+    if "e2e" in skip:
+        q_host = q_host[:128]
 
     def e2e_step(i):
         n = 0
@@ -409,8 +412,8 @@ def run_own(args):
         c_oracle.build()
         feed = orc.gmm_feed(*orc.get_3d_grid_gmm([RES] * 3, VARIANCE))
         tree = orc.build_kdtree(clouds_host[0])
-        sample = 1024
-        cpu_reference_pass(clouds_host[0], tree, cpu_sample_queries(0, 64), feed)
+        sample = 1024 if "cpu" not in skip else 16
+        cpu_reference_pass(clouds_host[0], tree, cpu_sample_queries(0, 64 if "cpu" not in skip else 8), feed)
         c0 = time.perf_counter()
         done = cpu_reference_pass(clouds_host[0], tree, cpu_sample_queries(1, sample), feed)
         cdt = time.perf_counter() - c0
