@@ -21,6 +21,43 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int library_pool(int device, cudaMemPool_t* pool) {
+    static std::mutex mtx;
+    static cudaMemPool_t pools[64] = {nullptr};
+    MUPS_REQUIRE(device >= 0 && device < 64, "device %d out of range", device);
+    std::lock_guard<std::mutex> lock(mtx);
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t p = nullptr;
+        MUPS_CUDA_TRY(cudaMemPoolCreate(&p, &props));
+        uint64_t keep = ~0ull;
+        MUPS_CUDA_TRY(cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep));
+        pools[device] = p;
+    }
+    *pool = pools[device];
+    return MUPS_OK;
+}
+
+// remembers that `st` has work queued that reads the index (the event is re-recorded per call)
+static int note_use(const mups_index* ix, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(ix->use_mutex);
+    for (auto& u : ix->uses) {
+        if (u.first == st) {
+            MUPS_CUDA_TRY(cudaEventRecord(u.second, st));
+            return MUPS_OK;
+        }
+    }
+    cudaEvent_t ev = nullptr;
+    MUPS_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    MUPS_CUDA_TRY(cudaEventRecord(ev, st));
+    ix->uses.emplace_back(st, ev);
+    return MUPS_OK;
+}
+
 static int check_device(int handle_device, const char* what) {
     int dev = -1;
     MUPS_CUDA_TRY(cudaGetDevice(&dev));
@@ -60,12 +97,18 @@ void mups_index_destroy(mups_index* ix) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(ix->device);
-    if (ix->built) { cudaEventSynchronize(ix->built); cudaEventDestroy(ix->built); }
-    cudaFree(ix->grid);
-    cudaFree(ix->sorted);
-    cudaFree(ix->cell_start);
-    cudaFree(ix->pos_of);
-    cudaFree(ix->codes);
+    // stream-ordered: the frees are queued on the build stream behind every stream that queried the index;
+    // nothing here blocks the host or synchronises the device
+    for (auto& u : ix->uses) {
+        if (u.first != ix->build_stream) cudaStreamWaitEvent(ix->build_stream, u.second, 0);
+        cudaEventDestroy(u.second);
+    }
+    if (ix->built) cudaEventDestroy(ix->built);
+    if (ix->grid) cudaFreeAsync(ix->grid, ix->build_stream);
+    if (ix->sorted) cudaFreeAsync(ix->sorted, ix->build_stream);
+    if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->build_stream);
+    if (ix->pos_of) cudaFreeAsync(ix->pos_of, ix->build_stream);
+    if (ix->codes) cudaFreeAsync(ix->codes, ix->build_stream);
     if (prev >= 0) cudaSetDevice(prev);
     delete ix;
 }
@@ -98,10 +141,13 @@ int mups_index_create(mups_index** out, const float* xyz_dev, int64_t n, double 
     const int64_t ncode = (int64_t)1 << (3 * bits);
     const int64_t n_scan = ncode + 1;
     const int64_t n_tiles = (n_scan + 2047) / 2048;
+    cudaMemPool_t pool = nullptr;
+    ix->build_stream = st;
+    if ((rc = library_pool(ix->device, &pool))) return fail(rc);
     auto alloc = [&](void** p, size_t bytes) -> int {
-        cudaError_t e = cudaMalloc(p, bytes);
+        cudaError_t e = cudaMallocFromPoolAsync(p, bytes, pool, st);
         if (e != cudaSuccess) {
-            set_error("mups_index_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            set_error("mups_index_create: allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
             return e == cudaErrorMemoryAllocation ? MUPS_ERR_NOMEM : MUPS_ERR_CUDA;
         }
         return MUPS_OK;
@@ -154,8 +200,10 @@ int mups_ball_query(const mups_index* ix, const int64_t* query_idx_dev, int64_t 
     if (int rc = check_device(ix->device, "mups_ball_query")) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (st != ix->build_stream) MUPS_CUDA_TRY(cudaStreamWaitEvent(st, ix->built, 0));
-    return launch_ball_query(ix, query_idx_dev, B, r_abs_host, S, P, seed, nbr_idx_dev, nbr_total_dev, patches_dev,
-                             n_eff_dev, st);
+    if (int rc = launch_ball_query(ix, query_idx_dev, B, r_abs_host, S, P, seed, nbr_idx_dev, nbr_total_dev, patches_dev,
+                                   n_eff_dev, st))
+        return rc;
+    return note_use(ix, st);
 }
 
 // ---- GMM ---------------------------------------------------------------------------------------
@@ -281,7 +329,11 @@ int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_e
     // stream-ordered scratch for the fast path's fallback worklist (1 counter + one id per (query, scale))
     int* work = nullptr;
     if (gmm->separable && !(flags & MUPS_FLAG_NO_FASTPATH) && B > 0)
-        MUPS_CUDA_TRY(cudaMallocAsync((void**)&work, sizeof(int) * (size_t)(B * S + 1), st));
+    {
+        cudaMemPool_t pool = nullptr;
+        if (int prc = library_pool(gmm->device, &pool)) return prc;
+        MUPS_CUDA_TRY(cudaMallocFromPoolAsync((void**)&work, sizeof(int) * (size_t)(B * S + 1), pool, st));
+    }
     const int rc = launch_3dmfv(gmm, patches_dev, n_eff_dev, B, S, P, flags, out_dev, work, st);
     if (work) cudaFreeAsync(work, st);
     return rc;

@@ -7,6 +7,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "../../include/mups.h"
 
@@ -74,6 +77,9 @@ struct mups_index {
     // host copy of the bbox, fetched lazily by mups_index_bbox
     mutable bool have_bbox = false;
     mutable float bb[6] = {0, 0, 0, 0, 0, 0};
+    // streams that have queried the index (one re-recorded event each): destroy orders the frees after them
+    mutable std::mutex use_mutex;
+    mutable std::vector<std::pair<cudaStream_t, cudaEvent_t>> uses;
 };
 
 struct mups_gmm {
@@ -93,6 +99,10 @@ struct mups_gmm {
 };
 
 namespace mups {
+
+// library-private stream-ordered memory pool of a device (release threshold = keep everything): index
+// buffers and scratch are allocated and freed without touching the OS or synchronising the device
+int library_pool(int device, cudaMemPool_t* pool);
 
 // kernels' host launchers (defined in the .cu files)
 int launch_index_build(mups_index* ix, const float* xyz, cudaStream_t st);

@@ -339,10 +339,13 @@ __device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 
 // (<= 8 distinct j, <= 4 distinct i, one k-quad) are bank-conflict free.
 // LOG_RES: the lattice is RES x RES x RES with RES = 1 << LOG_RES in {4, 8, 16, 32} (get_3d_grid_gmm is always
 // called with [n, n, n]); other lattices take the general kernel.
-template <int MINB, bool PACKED_SUMS, int LOG_RES>
+// MODE 0: packed FMUL2 products + scalar sums; 1: packed products + packed sums; 2: all scalar (more
+// instructions, but none that needs four distinct source registers)
+template <int MINB, int MODE, int LOG_RES>
 __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(const StatsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NT = kSepThreads, TPP = kSepTilePoints / 2;
+    constexpr bool PACKED_SUMS = MODE == 1;
     constexpr int RES = 1 << LOG_RES;
     constexpr int nx = RES, ny = RES, nz = RES;
     float4* FA[3];
@@ -466,31 +469,54 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                 for (int pp = 0; pp < npairs; ++pp, pxa += nx, pya += ny, pza += nz, pxb += nx, pyb += ny, pzb += nz) {
                     const float4 fx = *pxa, fy = *pya;
                     const float2 bx = *pxb, by = *pyb;
-                    const u64 qx = pack2(fx.x, fx.y), ax_ = pack2(fx.z, fx.w), bx_ = pack2(bx.x, bx.y);
-                    const u64 qy = pack2(fy.x, fy.y), ay_ = pack2(fy.z, fy.w), by_ = pack2(by.x, by.y);
-                    const u64 u_qq = mul2(qx, qy), u_aq = mul2(ax_, qy), u_qa = mul2(qx, ay_), u_bq = mul2(bx_, qy),
-                              u_qb = mul2(qx, by_);
+                    if (MODE == 2) {
+                        // all scalar; products grouped so that consecutive multiplies share a source register
+                        float u0[5], u1[5];      // qq, aq, qa, bq, qb of point 0 / point 1
+                        u0[0] = fx.x * fy.x; u0[1] = fx.z * fy.x; u0[3] = bx.x * fy.x; u0[2] = fx.x * fy.z; u0[4] = fx.x * by.x;
+                        u1[0] = fx.y * fy.y; u1[1] = fx.w * fy.y; u1[3] = bx.y * fy.y; u1[2] = fx.y * fy.w; u1[4] = fx.y * by.y;
 #pragma unroll
-                    for (int g = 0; g < kSepKPT; ++g) {
-                        const float4 fz = pza[g];
-                        const float2 bz = pzb[g];
-                        const u64 qz = pack2(fz.x, fz.y), az_ = pack2(fz.z, fz.w), bz_ = pack2(bz.x, bz.y);
-                        u64 t[7];
-                        t[0] = mul2(u_qq, qz);     // Q
-                        t[1] = mul2(u_aq, qz);     // Q t_x
-                        t[2] = mul2(u_qa, qz);     // Q t_y
-                        t[3] = mul2(u_qq, az_);    // Q t_z
-                        t[4] = mul2(u_bq, qz);     // Q (t_x^2 - 1)
-                        t[5] = mul2(u_qb, qz);     // Q (t_y^2 - 1)
-                        t[6] = mul2(u_qq, bz_);    // Q (t_z^2 - 1)
+                        for (int g = 0; g < kSepKPT; ++g) {
+                            const float4 fz = pza[g];
+                            const float2 bz = pzb[g];
+                            float v0[7], v1[7];
+                            v0[0] = u0[0] * fz.x; v0[3] = u0[0] * fz.z; v0[6] = u0[0] * bz.x;
+                            v0[1] = u0[1] * fz.x; v0[2] = u0[2] * fz.x; v0[4] = u0[3] * fz.x; v0[5] = u0[4] * fz.x;
+                            v1[0] = u1[0] * fz.y; v1[3] = u1[0] * fz.w; v1[6] = u1[0] * bz.y;
+                            v1[1] = u1[1] * fz.y; v1[2] = u1[2] * fz.y; v1[4] = u1[3] * fz.y; v1[5] = u1[4] * fz.y;
 #pragma unroll
-                        for (int c = 0; c < 7; ++c) {
-                            float lo, hi;
-                            unpack2(t[c], lo, hi);
-                            if (PACKED_SUMS) sm[g][c] = add2(sm[g][c], t[c]);
-                            else ss[g][c] = (ss[g][c] + lo) + hi;
-                            mx[g][c] = fmax3(mx[g][c], lo, hi);
-                            if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo, hi);
+                            for (int c = 0; c < 7; ++c) {
+                                ss[g][c] = (ss[g][c] + v0[c]) + v1[c];
+                                mx[g][c] = fmax3(mx[g][c], v0[c], v1[c]);
+                                if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], v0[c], v1[c]);
+                            }
+                        }
+                    } else {
+                        const u64 qx = pack2(fx.x, fx.y), ax_ = pack2(fx.z, fx.w), bx_ = pack2(bx.x, bx.y);
+                        const u64 qy = pack2(fy.x, fy.y), ay_ = pack2(fy.z, fy.w), by_ = pack2(by.x, by.y);
+                        const u64 u_qq = mul2(qx, qy), u_aq = mul2(ax_, qy), u_qa = mul2(qx, ay_), u_bq = mul2(bx_, qy),
+                                  u_qb = mul2(qx, by_);
+#pragma unroll
+                        for (int g = 0; g < kSepKPT; ++g) {
+                            const float4 fz = pza[g];
+                            const float2 bz = pzb[g];
+                            const u64 qz = pack2(fz.x, fz.y), az_ = pack2(fz.z, fz.w), bz_ = pack2(bz.x, bz.y);
+                            u64 t[7];
+                            t[0] = mul2(u_qq, qz);     // Q
+                            t[1] = mul2(u_aq, qz);     // Q t_x
+                            t[2] = mul2(u_qa, qz);     // Q t_y
+                            t[3] = mul2(u_qq, az_);    // Q t_z
+                            t[4] = mul2(u_bq, qz);     // Q (t_x^2 - 1)
+                            t[5] = mul2(u_qb, qz);     // Q (t_y^2 - 1)
+                            t[6] = mul2(u_qq, bz_);    // Q (t_z^2 - 1)
+#pragma unroll
+                            for (int c = 0; c < 7; ++c) {
+                                float lo, hi;
+                                unpack2(t[c], lo, hi);
+                                if (PACKED_SUMS) sm[g][c] = add2(sm[g][c], t[c]);
+                                else ss[g][c] = (ss[g][c] + lo) + hi;
+                                mx[g][c] = fmax3(mx[g][c], lo, hi);
+                                if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo, hi);
+                            }
                         }
                     }
                 }
@@ -633,10 +659,12 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
         else if (a.shift[0] == 4) MUPS_LAUNCH_SEP(MINB, PACKED, 4);                                                 \
         else MUPS_LAUNCH_SEP(MINB, PACKED, 5);                                                                      \
     } while (0)
-    if (variant == 2) MUPS_LAUNCH_SEP_RES(2, true);
-    else if (variant == 3) MUPS_LAUNCH_SEP_RES(3, true);
-    else if (variant == 5) MUPS_LAUNCH_SEP_RES(3, false);
-    else MUPS_LAUNCH_SEP_RES(4, false);
+    if (variant == 2) MUPS_LAUNCH_SEP_RES(2, 1);
+    else if (variant == 3) MUPS_LAUNCH_SEP_RES(3, 1);
+    else if (variant == 5) MUPS_LAUNCH_SEP_RES(3, 0);
+    else if (variant == 6) MUPS_LAUNCH_SEP_RES(4, 2);
+    else if (variant == 7) MUPS_LAUNCH_SEP_RES(3, 2);
+    else MUPS_LAUNCH_SEP_RES(4, 0);
 #undef MUPS_LAUNCH_SEP_RES
 #undef MUPS_LAUNCH_SEP
     MUPS_CHECK_LAUNCH();

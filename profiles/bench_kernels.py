@@ -58,7 +58,7 @@ def main():
     reps = int(os.environ.get("REPS", 2))
     for rep in range(reps):
         for name, variant, fast in (("general", 0, False), ("sep_minb4_scalar", 0, True), ("sep_minb3_scalar", 5, True),
-                                    ("sep_minb3_packed", 3, True), ("sep_minb2_packed", 2, True)):
+                                    ("sep_minb3_packed", 3, True), ("sep_minb4_allscalar", 6, True), ("sep_minb3_allscalar", 7, True)):
             if rep and name == "general":
                 continue
             _lib.set_option("stats_variant", variant)
