@@ -193,6 +193,7 @@ def run_reference(args):
     from oracle import c_oracle
     from oracle import mups_oracle as orc
     c_oracle.build()
+    c_oracle.set_num_threads(os.cpu_count())        # torchrun exports OMP_NUM_THREADS=1
     sample = 512
     clouds = [orc.synthetic_cloud(N_POINTS, cloud_id=i) for i in range(N_CLOUDS)]
     trees = [orc.build_kdtree(p) for p in clouds]
@@ -214,7 +215,7 @@ def run_reference(args):
                             "sample": "%d strided query points of the 100k per step (kd-tree build excluded); "
                                       "cKDTree.query_ball_point(workers=-1) + oracle C port (OpenMP) of get_3dmfv_n_est" % sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -420,10 +421,13 @@ def run_own(args):
            "h2d_bytes_per_step": pipe.h2d_bytes // e2e_steps, "d2h_bytes_per_step": pipe.d2h_bytes // e2e_steps,
            "api": "MuPSPipeline.features_to_host (pinned host cloud in, MuPS rows streamed to pinned host memory)"}
 
-    if rank == 0:
+    cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                    "sample": "measured at N=1 only (see the N=1 line / --impl reference)"}
+    if rank == 0 and n_gpus == 1:
         # ---- CPU baseline on a bounded sample (the oracle is the thing timed here, never the product) ----
         from oracle import c_oracle
         c_oracle.build()
+        c_oracle.set_num_threads(os.cpu_count())
         feed = orc.gmm_feed(*orc.get_3d_grid_gmm([RES] * 3, VARIANCE))
         tree = orc.build_kdtree(clouds_host[0])
         sample = 1024 if "cpu" not in skip else 16
@@ -435,16 +439,32 @@ def run_own(args):
                         "kind": "port",
                         "sample": "%d strided query points of cloud 0 (kd-tree build excluded); cKDTree.query_ball_point("
                                   "workers=-1) + oracle C port (OpenMP) of get_3dmfv_n_est" % sample}
+    if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config(n_gpus), "roofline": roofline,
                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, on the real stdout."""
+    f = _JSON_OUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
 def main():
+    global _JSON_OUT
+    # Library chatter (e.g. NCCL's version banner) is written to file descriptor 1 by C code: keep a private
+    # handle on the real stdout for the JSON line and point fd 1 at stderr for everything else.
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

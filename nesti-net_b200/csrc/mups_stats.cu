@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                 const float* ctile = coords + 3 * tile0;
                 const int last = tile_pts - 1;                                     // last real point of the tile
                 bool bad = false;
+#pragma unroll 3
                 for (int base = 0; base < total; base += NT) {
                     const int idx = base + tid;
                     const int li = idx & (RES - 1);

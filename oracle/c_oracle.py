@@ -38,6 +38,8 @@ def lib():
                                             ctypes.POINTER(ctypes.c_uint32)]
         L.oracle_selection_keys.restype = None
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_num_threads.restype = None
         _LIB = L
     return _LIB
 
@@ -52,6 +54,11 @@ def _i(a):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    lib().oracle_set_num_threads(int(n))
 
 
 def get_3dmfv(points, w, mu, sigma, n_eff=None, masked=True):
