@@ -8,8 +8,8 @@
 //   scan     the points of the (2R+1)^3 candidate cells are one flat range list, strided by the
 //            whole CTA (coalesced float4 loads, balanced); neighbours are counted per radius and
 //            appended to a shared-memory hit list (position + radius mask)
-//   select   only for radii with more than P neighbours: philox keys of the listed hits (dense, no
-//            divergence) -> 10-bit radix histogram -> threshold bin -> everything below is taken,
+//   select   only for radii with more than P neighbours: keys of the listed hits (a bijection of the
+//            point index salted per patch by Philox; dense loop, no divergence) -> 10-bit radix histogram -> threshold bin -> everything below is taken,
 //            the threshold group is resolved by rank counting (deeper radix levels if it is large)
 //   order    the <= P selected neighbours of each radius are bucket-sorted by point index
 //   K4       gather, centre on the query point, divide by float32(r), zero padding
@@ -72,7 +72,7 @@ __device__ __forceinline__ bool inside_exact(const QueryCtx& c, const float4& p,
 
 // Visits every neighbour of the centre (any radius): f(position in sorted, original index, bitmask of radii).
 // Block-wide: contains __syncthreads(); every thread of the CTA must call it.
-template <class F>
+template <int NS, class F>
 __device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx& c, ScanTables& st, F&& f) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int nx = c.x1 - c.x0 + 1, ny = c.y1 - c.y0 + 1, nz = c.z1 - c.z0 + 1;
@@ -122,12 +122,16 @@ __device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx&
             const float dx = p.x - c.cx, dy = p.y - c.cy, dz = p.z - c.cz;
             const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             if (d2 > a.r2_hi_max) continue;
-            uint32_t in = 0;
+            uint32_t in = 0, band = 0;      // inside for sure / inside the fp32 guard band of a radius
 #pragma unroll
-            for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
-                if (s < a.S && d2 <= a.r2_hi[s]) {
-                    if (d2 < a.r2_lo[s] || inside_exact(c, p, a.r2[s])) in |= 1u << s;
-                }
+            for (int s = 0; s < NS; ++s) {
+                in |= (d2 < a.r2_lo[s] ? 1u : 0u) << s;
+                band |= (d2 >= a.r2_lo[s] && d2 <= a.r2_hi[s] ? 1u : 0u) << s;
+            }
+            if (band) {                     // rare: decide with cKDTree's float64 predicate
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if ((band >> s) & 1u) in |= (inside_exact(c, p, a.r2[s]) ? 1u : 0u) << s;
             }
             if (in) f(i, (uint32_t)__float_as_int(p.w), in);
         }
@@ -135,17 +139,21 @@ __device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx&
     }
 }
 
-// key of neighbour `idx` for radius s: word s&3 of philox(counter = (idx, centre, s>>2, 0))
-__device__ __forceinline__ void selection_keys(const QueryArgs& a, uint32_t center, uint32_t idx, uint32_t need_mask,
+// key of neighbour `idx` for radius s: fmix32((idx ^ a_s) * b_s), a bijection of idx keyed by the salt
+// (a_s, b_s | 1) = Philox4x32-10(counter = (centre, s, 0, 0), key = seed) computed once per CTA and radius
+struct Salts {
+    uint32_t a[MUPS_MAX_SCALES], b[MUPS_MAX_SCALES];
+};
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+template <int NS>
+__device__ __forceinline__ void selection_keys(const Salts& salt, uint32_t idx, uint32_t need_mask,
                                                uint32_t key[MUPS_MAX_SCALES]) {
-    if (need_mask & 0x0Fu) {
-        const uint4 w = philox4x32_10(idx, center, 0u, 0u, a.k0, a.k1);
-        key[0] = w.x; key[1] = w.y; key[2] = w.z; key[3] = w.w;
-    }
-    if (need_mask & 0xF0u) {
-        const uint4 w = philox4x32_10(idx, center, 1u, 0u, a.k0, a.k1);
-        key[4] = w.x; key[5] = w.y; key[6] = w.z; key[7] = w.w;
-    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        if (need_mask & (1u << s)) key[s] = fmix32((idx ^ salt.a[s]) * salt.b[s]);
 }
 
 // One warp finds, in hist[0..nbins), the bin T holding the `need`-th smallest element.
@@ -206,9 +214,11 @@ __device__ __forceinline__ void block_scan_bins(uint32_t* bins, uint32_t* warp_s
     __syncthreads();
 }
 
+template <int NS>
 __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int S = a.S, P = a.P, Ppad = a.Ppad;
+    constexpr int S = NS;
+    const int P = a.P, Ppad = a.Ppad;
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);                                  // [S][kBins]
     unsigned long long* sel = reinterpret_cast<unsigned long long*>(hist + S * kBins);       // [S][Ppad]  (idx << 32 | pos)
     unsigned long long* bnd = sel + (size_t)S * Ppad;                                        // [S][kBoundaryCap] (key << 32 | idx)
@@ -224,6 +234,7 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
     __shared__ uint32_t s_min[MUPS_MAX_SCALES], s_max[MUPS_MAX_SCALES];
     __shared__ uint32_t s_unresolved, s_nhits;
     __shared__ uint32_t s_warp_sums[kQT / 32];
+    __shared__ Salts salt;
 
     const int64_t b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -262,22 +273,27 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
         c.y0 = max(iy - R, 0); c.y1 = min(iy + R, g.dims[1] - 1);
         c.z0 = max(iz - R, 0); c.z1 = min(iz + R, g.dims[2] - 1);
     }
+    if (tid < S) {   // per-patch randomness: one Philox call per radius
+        const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)tid, 0u, 0u, a.k0, a.k1);
+        salt.a[tid] = w.x;
+        salt.b[tid] = w.y | 1u;
+    }
     __syncthreads();
 
     // ---- scan: neighbour count per radius + hit list ---------------------------------------------
     {
         uint32_t cnt[MUPS_MAX_SCALES];
 #pragma unroll
-        for (int s = 0; s < MUPS_MAX_SCALES; ++s) cnt[s] = 0u;
-        for_each_hit(a, c, st, [&](uint32_t pos, uint32_t, uint32_t in) {
+        for (int s = 0; s < NS; ++s) cnt[s] = 0u;
+        for_each_hit<NS>(a, c, st, [&](uint32_t pos, uint32_t, uint32_t in) {
 #pragma unroll
-            for (int s = 0; s < MUPS_MAX_SCALES; ++s) cnt[s] += (in >> s) & 1u;
+            for (int s = 0; s < NS; ++s) cnt[s] += (in >> s) & 1u;
             const uint32_t slot = atomicAdd(&s_nhits, 1u);
             if (slot < (uint32_t)kHitCap) { hit_pos[slot] = pos; hit_mask[slot] = (unsigned char)in; }
         });
 #pragma unroll
-        for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
-            if (s < S) {
+        for (int s = 0; s < NS; ++s) {
+            {
                 uint32_t v = cnt[s];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
             }
             __syncthreads();
         } else {
-            for_each_hit(a, c, st, [&](uint32_t pos, uint32_t idx, uint32_t in) { if (in & want) f(pos, idx, in); });
+            for_each_hit<NS>(a, c, st, [&](uint32_t pos, uint32_t idx, uint32_t in) { if (in & want) f(pos, idx, in); });
         }
     };
 
@@ -312,9 +328,9 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
         visit(over, [&](uint32_t, uint32_t idx, uint32_t in) {
             in &= over;
             uint32_t key[MUPS_MAX_SCALES];
-            selection_keys(a, c.center, idx, in, key);
+            selection_keys<NS>(salt, idx, in, key);
 #pragma unroll
-            for (int s = 0; s < MUPS_MAX_SCALES; ++s)
+            for (int s = 0; s < NS; ++s)
                 if (in & (1u << s)) atomicAdd(hist + s * kBins + (key[s] >> (32 - kBinBits)), 1u);
         });
         // ---- radix threshold (warp s handles radius s) ----------------------------------------------------
@@ -338,9 +354,9 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
             visit(unresolved, [&](uint32_t, uint32_t idx, uint32_t in) {
                 in &= unresolved;
                 uint32_t key[MUPS_MAX_SCALES];
-                selection_keys(a, c.center, idx, in, key);
+                selection_keys<NS>(salt, idx, in, key);
 #pragma unroll
-                for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+                for (int s = 0; s < NS; ++s) {
                     if (in & (1u << s)) {
                         const uint32_t bits = s_bits[s];
                         const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
@@ -368,9 +384,9 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
     // ---- collect the selection ----------------------------------------------------------------------------
     visit(0xFFu, [&](uint32_t pos, uint32_t idx, uint32_t in) {
         uint32_t key[MUPS_MAX_SCALES];
-        selection_keys(a, c.center, idx, in & over, key);
+        selection_keys<NS>(salt, idx, in & over, key);
 #pragma unroll
-        for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             if (!(in & (1u << s))) continue;
             bool take = true;
             if (over & (1u << s)) {
@@ -522,10 +538,18 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
         set_error("ball query: S=%d, P=%d needs %zu bytes of shared memory", S, P, smem);
         return MUPS_ERR_UNSUPPORTED;
     }
-    if (smem > 48 * 1024)
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (B > 0) {
-        ball_query_kernel<<<(unsigned)B, kQT, smem, st>>>(a);
+#define MUPS_LAUNCH_QUERY(NS)                                                                                          \
+    case NS:                                                                                                           \
+        if (smem > 48 * 1024)                                                                                          \
+            MUPS_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ball_query_kernel<NS><<<(unsigned)B, kQT, smem, st>>>(a);                                                      \
+        break;
+        switch (S) {
+            MUPS_LAUNCH_QUERY(1) MUPS_LAUNCH_QUERY(2) MUPS_LAUNCH_QUERY(3) MUPS_LAUNCH_QUERY(4)
+            MUPS_LAUNCH_QUERY(5) MUPS_LAUNCH_QUERY(6) MUPS_LAUNCH_QUERY(7) MUPS_LAUNCH_QUERY(8)
+        }
+#undef MUPS_LAUNCH_QUERY
         MUPS_CHECK_LAUNCH();
     }
     return MUPS_OK;

@@ -181,21 +181,25 @@ int oracle_mups(const float* points, const int32_t* n_eff, const float* w, const
     return err;
 }
 
-/* Philox4x32-10 (Random123 constants) -- the shared seeded selection key,
- * see oracle/mups_oracle.py::selection_keys.  out[i] = key of neighbour nbr[i]. */
+/* The shared seeded selection key, see oracle/mups_oracle.py::selection_keys:
+ * (a, b) = first two words of Philox4x32-10(counter = (center, scale, 0, 0), key = seed);
+ * key(j) = fmix32((j ^ a) * (b | 1)).  out[i] = key of neighbour nbr[i]. */
+static uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
 void oracle_selection_keys(uint64_t seed, uint32_t center, uint32_t scale, const int32_t* nbr, int64_t n,
                            uint32_t* out) {
-    for (int64_t i = 0; i < n; ++i) {
-        uint32_t c0 = (uint32_t)nbr[i], c1 = center, c2 = scale >> 2, c3 = 0;
-        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-        for (int r = 0; r < 10; ++r) {
-            const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
-            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
-            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-        }
-        const uint32_t wds[4] = {c0, c1, c2, c3};
-        out[i] = wds[scale & 3];
+    uint32_t c0 = center, c1 = scale, c2 = 0, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
+    const uint32_t a = c0, b = c1 | 1u;
+    for (int64_t i = 0; i < n; ++i) out[i] = fmix32(((uint32_t)nbr[i] ^ a) * b);
 }
