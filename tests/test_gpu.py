@@ -414,3 +414,36 @@ def test_full_size_properties():
 def test_smoke_entry_point():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_downstream_moe_normals():
+    """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
+    models/experts_n_est.py, fp32, TF32 off) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4
+    angular RMS (degrees, the unit of utils/evaluate.py)."""
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pts = orc.synthetic_cloud(30000, cloud_id=9, noise=0.001)
+    radius = [0.01, 0.03, 0.05, 0.07]
+    P = 512
+    w, mu, sg = grid_gmm(8, 0.0156)
+    q = np.random.RandomState(8).choice(30000, 48, replace=False)
+    index = mb.PointIndex(pts, cell_frac=max(radius))
+    gpu_mups = mb.mups_features(index, mb.gmm_handle(w, mu, sg), q, index.absolute_radii(radius), P, seed=SEED)
+    o_patches, o_neff, _ = orc.gather_patches(pts, q, radius, P, seed=SEED)
+    ora_mups = torch.from_numpy(c_oracle.mups(o_patches, o_neff, w, mu, sg, 4)).cuda()
+    torch.manual_seed(1234)
+    net = ExpertsNormalEstimator(n_rads=4, n_gaussians=512, n_experts=7).cuda().eval()
+    with torch.no_grad():
+        prob_g, n_g = net(gpu_mups)
+        prob_o, n_o = net(ora_mups)
+    rms_all = angular_rms_deg(n_g.reshape(-1, 3), n_o.reshape(-1, 3))                # every expert's normal
+    sel_g, exp_g, _ = net.predict(gpu_mups)
+    sel_o, exp_o, _ = net.predict(ora_mups)
+    same = exp_g == exp_o
+    rms_sel = angular_rms_deg(sel_g[same], sel_o[same])
+    print("MoE normals: angular RMS %.3g deg over all experts, %.3g deg for the selected expert, "
+          "expert agreement %d/%d, max |dprob| %.3g" % (rms_all, rms_sel, int(same.sum()), len(q), float((prob_g - prob_o).abs().max())))
+    assert rms_all <= 1e-4 and rms_sel <= 1e-4
+    assert int(same.sum()) >= len(q) - 1          # a near-tie of two gate outputs may flip at most one query
+    assert float((prob_g - prob_o).abs().max()) < 1e-5

@@ -167,3 +167,38 @@ def test_dataset_rejects_options_off_the_hot_path(tmp_path):
         mb.pcpnet_dataset.PointcloudPatchDataset(use_pca=False, **dict(kw, patch_features=["bogus"]))
     with pytest.raises(ValueError):
         mb.provider.get_data_loader(outputs=["bogus"], indir=str(tmp_path), dataset_name="list.txt")
+
+
+def test_experts_net_tf_semantics_cpu():
+    """The PyTorch restatement of the MoE consumer: shapes, TF 'SAME' pooling semantics,
+    expert-to-scale assignment (models/experts_n_est.py:82-103)."""
+    from nesti_net_b200.experts_net import (ExpertsNormalEstimator, angular_rms_deg, avg_pool_same, max_pool_same)
+    torch.manual_seed(0)
+    y = torch.arange(27.).reshape(1, 1, 3, 3, 3)
+    ref = torch.zeros_like(y)
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                ref[0, 0, i, j, k] = y[0, 0, i:min(i + 2, 3), j:min(j + 2, 3), k:min(k + 2, 3)].mean()
+    assert torch.allclose(avg_pool_same(y, 2), ref)                  # even kernel: window extends after, valid cells only
+    assert torch.equal(avg_pool_same(y, 1), y)
+    mp = max_pool_same(y, 3, 2)                                       # 3 -> ceil(3/2) = 2, padded by one on both sides
+    assert tuple(mp.shape) == (1, 1, 2, 2, 2) and mp[0, 0, 0, 0, 0] == y[0, 0, :2, :2, :2].max() and mp.max() == 26
+    net = ExpertsNormalEstimator(n_rads=2, n_gaussians=27, n_experts=5).eval()
+    assert net.expert_dict == {0: [0], 1: [0], 2: [1], 3: [1], 4: [0, 1]}
+    assert net.expert_conv[4].mods[0].one.conv.in_channels == 40 and net.expert_conv[4].mods[0].one.conv.out_channels == 64
+    assert net.expert_conv[2].mods[0].one.conv.in_channels == 20
+    x = torch.randn(3, 3, 3, 3, 40) * 0.05
+    with torch.no_grad():
+        prob, n_est = net(x)
+        normal, expert, probs = net.predict(x)
+    assert tuple(prob.shape) == (5, 3) and tuple(n_est.shape) == (5, 3, 3) and torch.allclose(prob.sum(0), torch.ones(3))
+    assert tuple(normal.shape) == (3, 3) and torch.equal(expert, prob.argmax(0)) and tuple(probs.shape) == (3, 5)
+    # an expert only sees its own scales' channels
+    x2 = x.clone(); x2[..., 20:] += 1.0
+    with torch.no_grad():
+        _, n2 = net(x2)
+    assert torch.equal(n2[0], n_est[0]) and not torch.equal(n2[2], n_est[2])
+    assert angular_rms_deg(normal, -normal) < 1e-9 and abs(angular_rms_deg(torch.tensor([[1., 0, 0]]), torch.tensor([[0., 1, 0]])) - 90) < 1e-9
+    with pytest.raises(ValueError):
+        ExpertsNormalEstimator(n_rads=2, n_gaussians=125)
