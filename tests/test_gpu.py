@@ -418,22 +418,21 @@ def test_smoke_entry_point():
 
 def test_downstream_moe_normals():
     """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
-    models/experts_n_est.py, fp32, TF32 off) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4
-    angular RMS (degrees, the unit of utils/evaluate.py)."""
+    models/experts_n_est.py, fp32) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4 angular
+    RMS (degrees, the unit of utils/evaluate.py).  The network runs on the host: it is the checker here, and
+    cuDNN's strict-fp32 conv3d path on 8^3 volumes is two orders of magnitude slower than the CPU."""
     from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
     pts = orc.synthetic_cloud(30000, cloud_id=9, noise=0.001)
     radius = [0.01, 0.03, 0.05, 0.07]
     P = 512
     w, mu, sg = grid_gmm(8, 0.0156)
-    q = np.random.RandomState(8).choice(30000, 48, replace=False)
+    q = np.random.RandomState(8).choice(30000, 24, replace=False)
     index = mb.PointIndex(pts, cell_frac=max(radius))
-    gpu_mups = mb.mups_features(index, mb.gmm_handle(w, mu, sg), q, index.absolute_radii(radius), P, seed=SEED)
+    gpu_mups = mb.mups_features(index, mb.gmm_handle(w, mu, sg), q, index.absolute_radii(radius), P, seed=SEED).cpu()
     o_patches, o_neff, _ = orc.gather_patches(pts, q, radius, P, seed=SEED)
-    ora_mups = torch.from_numpy(c_oracle.mups(o_patches, o_neff, w, mu, sg, 4)).cuda()
+    ora_mups = torch.from_numpy(c_oracle.mups(o_patches, o_neff, w, mu, sg, 4))
     torch.manual_seed(1234)
-    net = ExpertsNormalEstimator(n_rads=4, n_gaussians=512, n_experts=7).cuda().eval()
+    net = ExpertsNormalEstimator(n_rads=4, n_gaussians=512, n_experts=7).eval()
     with torch.no_grad():
         prob_g, n_g = net(gpu_mups)
         prob_o, n_o = net(ora_mups)

@@ -186,7 +186,11 @@ def test_experts_net_tf_semantics_cpu():
     assert tuple(mp.shape) == (1, 1, 2, 2, 2) and mp[0, 0, 0, 0, 0] == y[0, 0, :2, :2, :2].max() and mp.max() == 26
     net = ExpertsNormalEstimator(n_rads=2, n_gaussians=27, n_experts=5).eval()
     assert net.expert_dict == {0: [0], 1: [0], 2: [1], 3: [1], 4: [0, 1]}
-    assert net.expert_conv[4].mods[0].one.conv.in_channels == 40 and net.expert_conv[4].mods[0].one.conv.out_channels == 64
+    # the 3^3 expert is conv_net_3g unchanged (no width divider, :276-277); the 8^3 expert divides (:254)
+    assert net.expert_conv[4].mods[0].one.conv.in_channels == 40 and net.expert_conv[4].mods[0].one.conv.out_channels == 128
+    net8 = ExpertsNormalEstimator(n_rads=4, n_gaussians=512, n_experts=7)
+    assert net8.expert_dict[6] == [0, 1, 2, 3] and net8.expert_conv[6].mods[0].one.conv.out_channels == 32
+    assert net8.expert_conv[0].mods[0].one.conv.out_channels == 128 and net8.gate_conv.out_features == 1536
     assert net.expert_conv[2].mods[0].one.conv.in_channels == 20
     x = torch.randn(3, 3, 3, 3, 40) * 0.05
     with torch.no_grad():
