@@ -1,0 +1,55 @@
+"""Inference driver: a list of `.xyz` clouds -> `.normals`, `.experts`, `.experts_probs` files.
+
+SURVEY.md 8(f) rank 2 ("next" row): the user-visible loop of the reference's
+test_n_est_w_experts.py:108-197 -- iterate every patch of every shape in 'full' order, compute
+MuPS, run the Mixture-of-Experts, keep the normal of the most probable expert, write one file
+triple per shape -- with the hot path on the GPU: batches come from one ball-query launch and one
+statistics launch, MuPS is consumed on the device and never stored.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import mups as _m
+from .provider import get_data_loader
+
+
+@torch.no_grad()
+def estimate_normals(indir, dataset_name, outdir, model, gmm, patch_radius, points_per_patch=512, batch_size=128,
+                     sparse_patches=False, seed=3627473, write=True):
+    """Returns {shape name: (normals [n,3], experts [n], experts_probs [n, n_experts])} and, when
+    `write`, saves them with np.savetxt exactly as test_n_est_w_experts.py:185-191 does.
+
+    model: nesti_net_b200.experts_net.ExpertsNormalEstimator (any device; MuPS is moved to it)
+    gmm:   GridGMM-like (weights_, means_, covariances_)"""
+    loader, dataset = get_data_loader(
+        dataset_name=dataset_name, batchSize=batch_size, indir=indir, patch_radius=patch_radius,
+        points_per_patch=points_per_patch, outputs=[], patch_point_count_std=0, seed=seed, identical_epochs=False,
+        use_pca=False, patch_center='point', point_tuple=1, cache_capacity=100, patch_sample_order='full',
+        workers=0, dataset_type='test', sparse_patches=sparse_patches)
+    handle = _m.gmm_handle(gmm.weights_, gmm.means_, np.sqrt(gmm.covariances_))
+    model_device = next(model.parameters()).device
+    model.eval()
+    n_rads = len(patch_radius)
+    normals, experts, probs = [], [], []
+    for data in loader:
+        points, n_eff = data[0], data[-1]
+        mups = _m.stats_3dmfv(points, n_eff, handle, n_rads, masked=True, layout="mups")
+        normal, expert, prob = model.predict(mups.to(model_device))
+        normals.append(normal.float().cpu().numpy())
+        experts.append(expert.cpu().numpy())
+        probs.append(prob.float().cpu().numpy())
+    normals, experts, probs = np.concatenate(normals), np.concatenate(experts), np.concatenate(probs)
+    out, offset = {}, 0
+    if write and not os.path.exists(outdir):
+        os.makedirs(outdir)
+    for name, count in zip(dataset.shape_names, dataset.shape_patch_count):
+        sl = slice(offset, offset + count)
+        out[name] = (normals[sl], experts[sl], probs[sl])
+        if write:
+            np.savetxt(os.path.join(outdir, name + '.normals'), normals[sl])
+            np.savetxt(os.path.join(outdir, name + '.experts'), experts[sl].astype(int), fmt='%i')
+            np.savetxt(os.path.join(outdir, name + '.experts_probs'), probs[sl])
+        offset += count
+    return out

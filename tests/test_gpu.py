@@ -416,6 +416,38 @@ def test_smoke_entry_point():
     ge.smoke()
 
 
+def test_inference_driver(tmp_path):
+    """.xyz list -> .normals / .experts / .experts_probs (test_n_est_w_experts.py:108-197) on a 3^3 grid."""
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator
+    from nesti_net_b200.inference import estimate_normals
+    radius, P = [0.05, 0.1], 64
+    names = ["shape_a", "shape_b"]
+    clouds = [orc.synthetic_cloud(700, cloud_id=11), orc.synthetic_cloud(500, cloud_id=12)]
+    for name, pts in zip(names, clouds):
+        np.savetxt(tmp_path / (name + ".xyz"), pts, fmt="%.9g")
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    gmm = mb.get_3d_grid_gmm([3, 3, 3], 0.11)
+    torch.manual_seed(5)
+    model = ExpertsNormalEstimator(n_rads=2, n_gaussians=27, n_experts=3).eval()        # checker-sized, on the host
+    out = estimate_normals(str(tmp_path), "list.txt", str(tmp_path / "results"), model, gmm, radius, P, batch_size=256)
+    assert list(out) == names
+    w, mu, sg = orc.gmm_feed(gmm.weights_, gmm.means_, gmm.covariances_)
+    for name, pts in zip(names, clouds):
+        normals, experts, probs = out[name]
+        assert normals.shape == (len(pts), 3) and experts.shape == (len(pts),) and probs.shape == (len(pts), 3)
+        assert np.allclose(np.loadtxt(tmp_path / "results" / (name + ".normals")), normals, atol=1e-7)
+        assert np.array_equal(np.loadtxt(tmp_path / "results" / (name + ".experts")).astype(int), experts)
+        assert np.allclose(np.loadtxt(tmp_path / "results" / (name + ".experts_probs")).sum(1), 1.0, atol=1e-5)
+        # the same network on oracle MuPS of the same shape
+        o_patches, o_neff, _ = orc.gather_patches(pts, np.arange(len(pts)), radius, P, seed=SEED)
+        ref_mups = torch.from_numpy(orc.mups_assemble(o_patches, w, mu, sg, o_neff, 2))
+        ref_n, ref_e, _ = model.predict(ref_mups)
+        same = ref_e.numpy() == experts
+        assert same.mean() > 0.99
+        assert mb.experts_net.angular_rms_deg(torch.from_numpy(normals[same]), ref_n[same]) < 1e-3
+        assert mb.evaluate.evaluate_shape(normals, ref_n.numpy())["pgp5"] > 0.99
+
+
 def test_downstream_moe_normals():
     """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
     models/experts_n_est.py, fp32) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4 angular

@@ -169,6 +169,21 @@ def test_dataset_rejects_options_off_the_hot_path(tmp_path):
         mb.provider.get_data_loader(outputs=["bogus"], indir=str(tmp_path), dataset_name="list.txt")
 
 
+def test_evaluation_metrics():
+    """RMS angle / PGP5 / PGP10 as defined in the reference's utils/evaluate.py:133-154."""
+    ev = mb.evaluate
+    gt = np.array([[0, 0, 1.0], [0, 0, 2.0], [1.0, 0, 0], [0, 1.0, 0]])
+    pred = np.array([[0, 0, -3.0], [0, np.sin(np.deg2rad(7)), np.cos(np.deg2rad(7))], [1.0, 0, 0], [0, 0, 1.0]])
+    ang = ev.angle_errors_deg(pred, gt)
+    assert np.allclose(ang, [0, 7, 0, 90], atol=1e-9)
+    assert np.allclose(ev.angle_errors_deg(pred, gt, oriented=True), [180, 7, 0, 90], atol=1e-6)
+    assert abs(ev.rms_angle(pred, gt) - np.sqrt((49 + 8100) / 4.0)) < 1e-9
+    rec = ev.evaluate_shape(pred, gt)
+    assert rec["pgp5"] == 0.5 and rec["pgp10"] == 0.75 and rec["n"] == 4 and rec["rms_o"] > rec["rms"]
+    sparse = ev.evaluate_shape(pred, gt, pidx=[1, 2])
+    assert sparse["n"] == 2 and abs(sparse["rms"] - np.sqrt(49 / 2.0)) < 1e-9
+
+
 def test_experts_net_tf_semantics_cpu():
     """The PyTorch restatement of the MoE consumer: shapes, TF 'SAME' pooling semantics,
     expert-to-scale assignment (models/experts_n_est.py:82-103)."""
