@@ -55,6 +55,7 @@ def config(n_gpus):
             "clouds_per_step": n_gpus, "scales": RADIUS, "points_per_patch": P, "grid": "%dx%dx%d" % (RES, RES, RES),
             "gmm_variance": VARIANCE, "seed": SEED,
             "partitioning": "query points sharded across %d GPU(s), cloud replicated, per-rank slabs, no collective" % n_gpus,
+            "schedule": "half 1 of cloud i+1 (side stream) overlaps half 2 of cloud i (main stream); MUPS_BENCH_PIPELINE=0 serialises",
             "l2": "each step writes 16.4 GB of MuPS + 2.5 GB of patches per GPU (>> 126 MB L2) and cycles "
                   "through %d clouds; no explicit flush needed" % N_CLOUDS}
 
@@ -284,38 +285,67 @@ def run_own(args):
 
     stat_events = []
 
-    # The index of the next cloud is built on a high-priority side stream while the current cloud's kernels run, so
-    # the one small host read of the path (the bbox -> radii, evaluated with the reference's numpy expression) never
-    # leaves the GPU idle.  Every step still builds exactly one index per cloud inside the timed region.
+    # Software pipeline across clouds.  Half 1 of the NEXT cloud (index build, the one small host read of the path --
+    # bbox -> radii, evaluated with the reference's numpy expression -- and the ball-query kernel, which is latency /
+    # barrier bound) runs on a high-priority side stream while half 2 (the FP32-bound statistics kernel) of the CURRENT
+    # cloud runs on the main stream; patches are double buffered.  Every step still performs one index build, one ball
+    # query and one statistics launch per cloud inside the timed region.  MUPS_BENCH_PIPELINE=0 serialises them.
+    pipelined = os.environ.get("MUPS_BENCH_PIPELINE", "1") != "0"
     side = torch.cuda.Stream(dev, priority=-1)
+    side_ptr = ctypes.c_void_p(side.cuda_stream)
+    patches2 = [patches, torch.empty_like(patches) if pipelined else patches]
+    n_eff2 = [n_eff, torch.empty_like(n_eff) if pipelined else n_eff]
+    total2 = [total, torch.empty_like(total) if pipelined else total]
+    stats_done = [None, None]
 
-    def make_index(i, c):
+    def half1(i, c, slot):
         xyz = clouds_dev[(i * n_gpus + c) % len(clouds_dev)]
         with torch.cuda.stream(side):
             index = mb.PointIndex(xyz, cell_frac=max(RADIUS))
-        return index, np.ascontiguousarray(index.absolute_radii(RADIUS), dtype=np.float64)
+        radii = np.ascontiguousarray(index.absolute_radii(RADIUS), dtype=np.float64)
+        if not pipelined:
+            return index, radii, None
+        sl = slice(c * per_cloud, (c + 1) * per_cloud)
+        if stats_done[slot] is not None:
+            side.wait_event(stats_done[slot])            # the statistics kernel that last read this patch buffer
+        _lib.check(L.mups_ball_query(index.handle, ctypes.c_void_p(q_shard.data_ptr()), per_cloud,
+                                     radii.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), S, P, SEED, None,
+                                     ctypes.c_void_p(total2[slot][sl].data_ptr()), ctypes.c_void_p(patches2[slot][sl].data_ptr()),
+                                     ctypes.c_void_p(n_eff2[slot][sl].data_ptr()), side_ptr))
+        ev = torch.cuda.Event()
+        ev.record(side)
+        return index, radii, ev
 
-    prefetched = {"next": [make_index(0, c) for c in range(n_gpus)]}
+    prefetched = {"next": [half1(0, c, 0) for c in range(n_gpus)]}
 
     def step(i, timed):
         """One pass of the hot path: n_gpus clouds, this rank's query shard of each."""
+        slot = (i & 1) if pipelined else 0
         cur, nxt = prefetched["next"], []
         for c in range(n_gpus):
-            index, radii = cur[c]
+            index, radii, ev = cur[c]
             sl = slice(c * per_cloud, (c + 1) * per_cloud)
-            _lib.check(L.mups_ball_query(index.handle, ctypes.c_void_p(q_shard.data_ptr()), per_cloud,
-                                         radii.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), S, P, SEED, None,
-                                         ctypes.c_void_p(total[sl].data_ptr()), ctypes.c_void_p(patches[sl].data_ptr()),
-                                         ctypes.c_void_p(n_eff[sl].data_ptr()), sptr))
+            if pipelined:
+                stream.wait_event(ev)
+            else:
+                _lib.check(L.mups_ball_query(index.handle, ctypes.c_void_p(q_shard.data_ptr()), per_cloud,
+                                             radii.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), S, P, SEED, None,
+                                             ctypes.c_void_p(total[sl].data_ptr()), ctypes.c_void_p(patches[sl].data_ptr()),
+                                             ctypes.c_void_p(n_eff[sl].data_ptr()), sptr))
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            _lib.check(L.mups_3dmfv(gmm.handle, ctypes.c_void_p(patches[sl].data_ptr()), ctypes.c_void_p(n_eff[sl].data_ptr()),
-                                    per_cloud, S, P, _lib.FLAG_MASKED, ctypes.c_void_p(feats[sl].data_ptr()), sptr))
+            _lib.check(L.mups_3dmfv(gmm.handle, ctypes.c_void_p(patches2[slot][sl].data_ptr()),
+                                    ctypes.c_void_p(n_eff2[slot][sl].data_ptr()), per_cloud, S, P, _lib.FLAG_MASKED,
+                                    ctypes.c_void_p(feats[sl].data_ptr()), sptr))
             e1.record(stream)
             if timed:
                 stat_events.append((e0, e1))
-            nxt.append(make_index(i + 1, c))
+        done = torch.cuda.Event()
+        done.record(stream)
+        stats_done[slot] = done
+        for c in range(n_gpus):
+            nxt.append(half1(i + 1, c, slot ^ 1))
         prefetched["next"] = nxt
 
     def barrier():
@@ -351,7 +381,7 @@ def run_own(args):
     value = rows * n_gpus * args.steps / (ms_total * 1e-3)
 
     # the dominant kernel: statistics.  Algorithmic work of the last step's launches on this rank.
-    ne = n_eff.cpu().numpy()
+    ne = n_eff2[(args.warmup + args.steps - 1) & 1 if pipelined else 0].cpu().numpy()
     m_unmasked = np.where(ne >= P - 1, P, ne + 1).astype(np.int64)
     pairs_step = float(m_unmasked.sum()) * G
     stat_ms = float(np.mean([a.elapsed_time(b) for a, b in stat_events])) * n_gpus      # per step (n_gpus launches)
