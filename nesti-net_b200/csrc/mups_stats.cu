@@ -20,9 +20,13 @@
 // Both end with the same epilogue: masked-slot zeros, scale factors, /n_eff, signed square root,
 // per-channel L2 norm over the Gaussians (CTA-wide reduction), direct store into
 // [B, res, res, res, 20*S] (or channel-major).
+#include <cooperative_groups.h>
+
 #include "mups_common.cuh"
 
 namespace mups {
+
+namespace cg = cooperative_groups;
 
 struct StatsArgs {
     const float4* A;
@@ -324,6 +328,7 @@ __global__ void __launch_bounds__(NT) stats_general_kernel(const StatsArgs a) {
 constexpr int kSepThreads = 128;
 constexpr int kSepKPT = 4;              // Gaussians per thread, consecutive along z
 constexpr int kSepTilePoints = 128;     // points staged per tile (64 point pairs)
+constexpr int kSepClusterTilePoints = 64;   // cluster variant: smaller tiles keep 4 CTAs per SM at 16^3
 
 __device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 2^-23 (PTX ISA)
     float y;
@@ -341,10 +346,16 @@ __device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 
 // called with [n, n, n]); other lattices take the general kernel.
 // MODE 0: packed FMUL2 products + scalar sums; 1: packed products + packed sums; 2: all scalar (more
 // instructions, but none that needs four distinct source registers)
-template <int MINB, int MODE, int LOG_RES>
+//
+// CL > 1 (16^3 lattice: 1024 thread-tasks = 8 groups of 128): a thread-block CLUSTER of CL CTAs shares one
+// (query, scale).  CTA r owns task group r; the factor tables are staged once per cluster -- every CTA computes
+// 1/CL of the entries and writes them into all CL shared memories through distributed shared memory -- and the
+// per-channel sums of squares are exchanged the same way, so nothing is recomputed and nothing is re-read from HBM.
+template <int MINB, int MODE, int LOG_RES, int CL>
 __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(const StatsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NT = kSepThreads, TPP = kSepTilePoints / 2;
+    constexpr int TILE = CL > 1 ? kSepClusterTilePoints : kSepTilePoints;
+    constexpr int NT = kSepThreads, TPP = TILE / 2;
     constexpr bool PACKED_SUMS = MODE == 1;
     constexpr int RES = 1 << LOG_RES;
     constexpr int nx = RES, ny = RES, nz = RES;
@@ -360,12 +371,15 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
     float* red = lat + 3 * 64;                                 // [NT/32][20]
     float* inv_norm = red + (NT / 32) * 20;                    // [20] (+12 pad)
     float* axis_par = inv_norm + 20;                           // [3][4]: 1/sigma, guard lo, guard hi
-    float* coords = inv_norm + 32;                             // [3*P] the patch, staged once (coalesced)
+    float* cl_sq = inv_norm + 32;                              // [CL][20] per-CTA sums of squares (cluster exchange)
+    float* coords = cl_sq + (CL > 1 ? CL * 20 : 0);            // [3*P] the patch, staged once (coalesced)
     __shared__ int s_fallback;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = CL > 1 ? cluster.block_rank() : 0u;
 
     const int tid = threadIdx.x;
     const int S = a.S, P = a.P;
-    const int item = blockIdx.x;
+    const int item = CL > 1 ? blockIdx.x / CL : blockIdx.x;
     const int64_t b = item / S;
     const int s = item % S;
     const bool masked = (a.flags & MUPS_FLAG_MASKED) != 0;
@@ -390,13 +404,17 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
     constexpr int nxy = nx * ny;
     constexpr int tasks = nxy * nzq;
     constexpr int groups = (tasks + NT - 1) / NT;
+    static_assert(CL == 1 || CL == groups, "a cluster covers all task groups of one (query, scale)");
+    auto block_or_cluster_sync = [&]() {
+        if (CL > 1) cluster.sync(); else __syncthreads();
+    };
     float sq[20];
 #pragma unroll
     for (int c = 0; c < 20; ++c) sq[c] = 0.f;
     float v[kSepKPT][20];
-    __syncthreads();
+    block_or_cluster_sync();   // s_fallback is initialised in every CTA before anyone may raise it remotely
 
-    for (int group = 0; group < groups; ++group) {
+    for (int group = (CL > 1 ? (int)crank : 0); group < (CL > 1 ? (int)crank + 1 : groups); ++group) {
         // task -> (k-quad, i, j) with j fastest: a warp spans <= 8 j, <= 4 i and (nx*ny >= 32) one k-quad
         const int task = group * NT + tid;
         const bool valid = task < tasks;
@@ -415,17 +433,21 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
             for (int c = 0; c < 6; ++c) mn[g][c] = INFINITY;
         }
 
-        for (int tile0 = 0; tile0 < m; tile0 += kSepTilePoints) {
-            const int tile_pts = min(kSepTilePoints, m - tile0);
+        for (int tile0 = 0; tile0 < m; tile0 += TILE) {
+            const int tile_pts = min(TILE, m - tile0);
             const int npairs = (tile_pts + 1) >> 1;
             // ---- stage the per-axis factors of this tile: one lane per (point pair, axis, lattice index) ----
             {
                 const int total = (npairs * 3) << LOG_RES;
+                // a cluster splits the lane-tasks: CTA r stages [r * share, (r + 1) * share) for everyone
+                const int share = CL > 1 ? ((total + CL * NT - 1) / (CL * NT)) * NT : total;
+                const int first = CL > 1 ? (int)crank * share : 0;
+                const int stop = min(total, first + share);
                 const float* ctile = coords + 3 * tile0;
                 const int last = tile_pts - 1;                                     // last real point of the tile
                 bool bad = false;
 #pragma unroll 3
-                for (int base = 0; base < total; base += NT) {
+                for (int base = first; base < stop; base += NT) {
                     const int idx = base + tid;
                     const int li = idx & (RES - 1);
                     const int r = min(idx, total - 1) >> LOG_RES;                   // r = 3 * pair + axis (idle lanes clamp)
@@ -447,15 +469,31 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                     const float a0 = q0 * t0, a1 = q1 * t1;
                     if (idx < total) {
                         const int slot = ax * (TPP * RES) + (pp << LOG_RES) + li;   // FA[ax] / FB[ax] are contiguous
-                        FA[0][slot] = make_float4(q0, q1, a0, a1);
-                        FB[0][slot] = make_float2(fmaf(a0, t0, -q0), fmaf(a1, t1, -q1));
+                        const float4 fa = make_float4(q0, q1, a0, a1);
+                        const float2 fb = make_float2(fmaf(a0, t0, -q0), fmaf(a1, t1, -q1));
+                        if (CL > 1) {
+#pragma unroll
+                            for (int r = 0; r < CL; ++r) {       // distributed shared memory: every CTA of the cluster
+                                cluster.map_shared_rank(FA[0], r)[slot] = fa;
+                                cluster.map_shared_rank(FB[0], r)[slot] = fb;
+                            }
+                        } else {
+                            FA[0][slot] = fa;
+                            FB[0][slot] = fb;
+                        }
                     }
                     const float glo = axis_par[4 * ax + 1], ghi = axis_par[4 * ax + 2];
                     bad |= !(c0 >= glo && c0 <= ghi) || !(c1 >= glo && c1 <= ghi);   // outside the 5-sigma box (or NaN)
                 }
-                if (bad) s_fallback = 1;
+                if (bad) {
+                    if (CL > 1) {
+                        for (int r = 0; r < CL; ++r) *cluster.map_shared_rank(&s_fallback, r) = 1;
+                    } else {
+                        s_fallback = 1;
+                    }
+                }
             }
-            __syncthreads();
+            block_or_cluster_sync();
             if (s_fallback) break;
 
             // ---- 20 reductions x 4 Gaussians, two points per step -------------------------------------------
@@ -522,7 +560,7 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                     }
                 }
             }
-            __syncthreads();   // the factor tables are rewritten by the next tile
+            block_or_cluster_sync();   // the factor tables are rewritten by the next tile
         }
         if (s_fallback) break;
 
@@ -559,20 +597,36 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                 v[g][c] = r;
                 if (valid) sq[c] = fmaf(r, r, sq[c]);
             }
-            if (groups > 1 && valid) store_gaussian(a, b, s, (i * ny + j) * nz + k0 + g, v[g], nullptr);
+            if (CL == 1 && groups > 1 && valid) store_gaussian(a, b, s, (i * ny + j) * nz + k0 + g, v[g], nullptr);
         }
     }
 
-    if (s_fallback) {   // uniform: the whole CTA leaves, the general kernel redoes this (query, scale)
-        if (tid == 0) a.worklist[atomicAdd(a.work_count, 1)] = item;
+    if (s_fallback) {   // uniform over the CTA (and the cluster): everyone leaves, the general kernel redoes this item
+        if (tid == 0 && crank == 0) a.worklist[atomicAdd(a.work_count, 1)] = item;
         return;
     }
 
     channel_norms<NT>(sq, red, inv_norm);
+    if (CL > 1) {
+        // inv_norm holds rsqrt(max(own sum, eps)); exchange the raw per-CTA sums instead and redo the norm over the cluster
+        if (tid < 20) {
+            float x = 0.f;
+            for (int wq = 0; wq < NT / 32; ++wq) x += red[wq * 20 + tid];
+            for (int r = 0; r < CL; ++r) cluster.map_shared_rank(cl_sq, r)[crank * 20 + tid] = x;
+        }
+        cluster.sync();
+        if (tid < 20) {
+            float x = 0.f;
+            for (int r = 0; r < CL; ++r) x += cl_sq[r * 20 + tid];
+            inv_norm[tid] = 1.0f / sqrtf(fmaxf(x, 1e-12f));
+        }
+        __syncthreads();
+    }
 
-    if (groups == 1) {
-        if (tid < tasks) {
-            const int j = tid % ny, i = (tid / ny) % nx, kq = tid / nxy;
+    if (groups == 1 || CL > 1) {
+        const int task = (CL > 1 ? (int)crank * NT : 0) + tid;
+        if (task < tasks) {
+            const int j = task % ny, i = (task / ny) % nx, kq = task / nxy;
 #pragma unroll
             for (int g = 0; g < kSepKPT; ++g) store_gaussian(a, b, s, (i * ny + j) * nz + kq * kSepKPT + g, v[g], inv_norm);
         }
@@ -647,20 +701,40 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
     const size_t smem = (size_t)TPP * (a.res[0] + a.res[1] + a.res[2]) * (sizeof(float4) + sizeof(float2)) +
                         sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
     const int variant = g_stats_variant.load();
-#define MUPS_LAUNCH_SEP(MINB, PACKED, LOG)                                                                          \
+#define MUPS_LAUNCH_SEP(MINB, MODE, LOG)                                                                            \
     do {                                                                                                            \
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, PACKED, LOG>,                               \
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, MODE, LOG, 1>,                              \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-        stats_separable_kernel<MINB, PACKED, LOG><<<(unsigned)items, kSepThreads, smem, st>>>(a);                   \
+        stats_separable_kernel<MINB, MODE, LOG, 1><<<(unsigned)items, kSepThreads, smem, st>>>(a);                  \
     } while (0)
-#define MUPS_LAUNCH_SEP_RES(MINB, PACKED)                                                                           \
+#define MUPS_LAUNCH_SEP_RES(MINB, MODE)                                                                             \
     do {                                                                                                            \
-        if (a.shift[0] == 2) MUPS_LAUNCH_SEP(MINB, PACKED, 2);                                                      \
-        else if (a.shift[0] == 3) MUPS_LAUNCH_SEP(MINB, PACKED, 3);                                                 \
-        else if (a.shift[0] == 4) MUPS_LAUNCH_SEP(MINB, PACKED, 4);                                                 \
-        else MUPS_LAUNCH_SEP(MINB, PACKED, 5);                                                                      \
+        if (a.shift[0] == 2) MUPS_LAUNCH_SEP(MINB, MODE, 2);                                                        \
+        else if (a.shift[0] == 3) MUPS_LAUNCH_SEP(MINB, MODE, 3);                                                   \
+        else if (a.shift[0] == 4) MUPS_LAUNCH_SEP(MINB, MODE, 4);                                                   \
+        else MUPS_LAUNCH_SEP(MINB, MODE, 5);                                                                        \
     } while (0)
-    if (variant == 2) MUPS_LAUNCH_SEP_RES(2, 1);
+    if (a.shift[0] == 4 && variant != 8 && items * 8 <= 0x7FFFFFFFll) {
+        // 16^3 lattice: one thread-block cluster of 8 CTAs per (query, scale), tables shared through DSMEM
+        constexpr int kCl = 8;
+        auto kern = stats_separable_kernel<4, 0, 4, kCl>;
+        const size_t smem_cl = (size_t)(kSepClusterTilePoints / 2) * 3 * 16 * (sizeof(float4) + sizeof(float2)) +
+                               sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P + kCl * 20);
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(items * kCl));
+        cfg.blockDim = dim3(kSepThreads);
+        cfg.dynamicSmemBytes = smem_cl;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kCl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MUPS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+    } else if (variant == 2) MUPS_LAUNCH_SEP_RES(2, 1);
     else if (variant == 3) MUPS_LAUNCH_SEP_RES(3, 1);
     else if (variant == 5) MUPS_LAUNCH_SEP_RES(3, 0);
     else if (variant == 6) MUPS_LAUNCH_SEP_RES(4, 2);
