@@ -416,6 +416,44 @@ def test_smoke_entry_point():
     ge.smoke()
 
 
+def test_sharded_slabs_and_host_pipeline():
+    """Section 8e: per-rank slabs of a sharded query list concatenate to the single-GPU result bit for bit
+    (here the ranks run one after the other on one device), with and without work-balanced cuts; and the
+    host-buffer streaming API (MuPSPipeline.features_to_host) returns the same rows."""
+    n, P = 6000, 128
+    radius = [0.03, 0.08]
+    pts = orc.synthetic_cloud(n, cloud_id=13, kind="scan")
+    gmm = mb.get_3d_grid_gmm([8, 8, 8], 0.0156)
+    handle = mb.gmm_handle(gmm.weights_, gmm.means_, np.sqrt(gmm.covariances_))
+    index = mb.PointIndex(pts, cell_frac=max(radius))
+    radii = index.absolute_radii(radius)
+    q = np.arange(n, dtype=np.int64)
+    full, _, _, total = mb.mups_features(index, handle, q, radii, P, seed=SEED, return_patches=True)
+    work = total.cpu().numpy()[:, -1].astype(np.float64)            # neighbour count at the largest radius
+    for world, weights in ((4, None), (3, work)):
+        slabs = []
+        for rank in range(world):
+            mine, lo, hi = mb.dist.shard_queries(q, rank, world, weights)
+            slabs.append(mb.mups_features(index, handle, mine, radii, P, seed=SEED))
+        assert torch.equal(torch.cat(slabs), full)
+    bounds = mb.dist.shard_bounds(n, 3, work)
+    loads = [work[bounds[r]:bounds[r + 1]].sum() for r in range(3)]
+    assert max(loads) / (work.sum() / 3) < 1.05                    # balanced by estimated work, not by count
+    pipe = mb.MuPSPipeline(gmm, radius, P, seed=SEED, chunk=1024)
+    got = np.zeros((n, 20 * 2 * 512), np.float32)
+    seen = []
+
+    def consume(lo, hi, rows):
+        got[lo:hi] = rows
+        seen.append((lo, hi))
+    assert pipe.features_to_host(torch.from_numpy(pts).pin_memory(), None, consume) == n
+    assert sorted(seen) == [(lo, min(lo + 1024, n)) for lo in range(0, n, 1024)]
+    assert np.array_equal(got, full.cpu().numpy().reshape(n, -1))
+    assert pipe.d2h_bytes == got.nbytes and pipe.h2d_bytes == pts.nbytes
+    dev = pipe.features_on_device(pts, q[:100])
+    assert torch.equal(dev, full[:100])
+
+
 def test_inference_driver(tmp_path):
     """.xyz list -> .normals / .experts / .experts_probs (test_n_est_w_experts.py:108-197) on a 3^3 grid."""
     from nesti_net_b200.experts_net import ExpertsNormalEstimator
