@@ -9,7 +9,7 @@
 //            whole CTA (coalesced float4 loads, balanced); neighbours are counted per radius and
 //            appended to a shared-memory hit list (position + radius mask)
 //   select   only for radii with more than P neighbours: keys of the listed hits (a bijection of the
-//            point index salted per patch by Philox; dense loop, no divergence) -> 10-bit radix histogram -> threshold bin -> everything below is taken,
+//            point index salted per patch by Philox; dense loop, no divergence) -> 9-bit radix histogram -> threshold bin -> everything below is taken,
 //            the threshold group is resolved by rank counting (deeper radix levels if it is large)
 //   order    the <= P selected neighbours of each radius are bucket-sorted by point index
 //   K4       gather, centre on the query point, divide by float32(r), zero padding
@@ -19,9 +19,9 @@
 namespace mups {
 
 constexpr int kQT = 256;            // threads per query CTA
-constexpr int kBinBits = 10;
+constexpr int kBinBits = 9;
 constexpr int kBins = 1 << kBinBits;
-constexpr int kBoundaryCap = 256;   // max entries of the threshold radix group resolved by rank counting
+constexpr int kBoundaryCap = 128;   // max entries of the threshold radix group resolved by rank counting
 constexpr int kHitCap = 4096;       // neighbours (any radius) kept in the shared-memory hit list
 constexpr int kRangeCap = 64;       // candidate cells per scan batch
 
@@ -304,6 +304,17 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
     __syncthreads();
     const uint32_t nhits = s_nhits;
     const bool listed = nhits <= (uint32_t)kHitCap;     // else: every pass re-scans the cells
+    // threshold-group storage: the small dedicated lists, or -- when the hit list is unused (re-scan mode: dense
+    // balls, large groups) -- the hit-list region, which holds ~3x more entries and saves a refinement scan
+    uint32_t bcap = (uint32_t)kBoundaryCap;
+    unsigned long long* bndl = bnd;
+    uint32_t* bndp = bnd_pos;
+    if (!listed) {
+        bcap = ((uint32_t)(kHitCap * 5) / (12u * (uint32_t)S)) & ~7u;
+        bndl = reinterpret_cast<unsigned long long*>(shared_region);
+        bndp = reinterpret_cast<uint32_t*>(bndl + (size_t)S * bcap);
+    }
+    const uint32_t gcap = min((uint32_t)a.cap, bcap);   // largest group resolved without another radix level
     uint32_t over = 0;                                   // radii with more than P neighbours need keys
     for (int s = 0; s < S; ++s) over |= (s_cnt[s] > (uint32_t)P) ? (1u << s) : 0u;
 
@@ -339,11 +350,11 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
             warp_find_threshold(hist + warp * kBins, kBins, (uint32_t)P, lane, &T, &below, &group);
             if (lane == 0) {
                 s_prefix[warp] = T; s_bits[warp] = kBinBits; s_need[warp] = (uint32_t)P - below;
-                if (group > (uint32_t)a.cap) atomicOr(&s_unresolved, 1u << warp);
+                if (group > gcap) atomicOr(&s_unresolved, 1u << warp);
             }
         }
         __syncthreads();
-        // ---- refinement levels (only when a threshold group exceeds the cap: > ~250k neighbours) ----------
+        // ---- refinement levels (only when a threshold group exceeds the cap: > ~60k neighbours) ----------
         while (s_unresolved) {
             const uint32_t unresolved = s_unresolved;
             __syncthreads();
@@ -373,8 +384,8 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
                 if (lane == 0) {
                     s_prefix[warp] = (s_prefix[warp] << nb) | T; s_bits[warp] = bits + nb; s_need[warp] -= below;
                     // with all 32 key bits fixed the group is a set of exact key ties; more than the cap of
-                    // them cannot be told apart here (needs > 256 equal 32-bit keys in one ball)
-                    if (group > (uint32_t)a.cap && bits + nb < 32u) atomicOr(&s_unresolved, 1u << warp);
+                    // them cannot be told apart here (the keys are a bijection of the index, so this cannot happen)
+                    if (group > gcap && bits + nb < 32u) atomicOr(&s_unresolved, 1u << warp);
                 }
             }
             __syncthreads();
@@ -394,9 +405,9 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
                 take = hp < s_prefix[s];
                 if (hp == s_prefix[s]) {
                     const uint32_t slot = atomicAdd(s_nb + s, 1u);
-                    if (slot < (uint32_t)kBoundaryCap) {
-                        bnd[s * kBoundaryCap + slot] = ((unsigned long long)key[s] << 32) | idx;
-                        bnd_pos[s * kBoundaryCap + slot] = pos;
+                    if (slot < bcap) {
+                        bndl[s * bcap + slot] = ((unsigned long long)key[s] << 32) | idx;
+                        bndp[s * bcap + slot] = pos;
                     }
                 }
             }
@@ -410,16 +421,16 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
 
     // ---- threshold group: keep the `need` smallest (key, index) pairs ------------------------------------
     for (int s = 0; s < S; ++s) {
-        const uint32_t m = min(s_nb[s], (uint32_t)kBoundaryCap);
+        const uint32_t m = min(s_nb[s], bcap);
         const uint32_t need = s_need[s];
         for (uint32_t i = tid; i < m; i += kQT) {
-            const unsigned long long mine = bnd[s * kBoundaryCap + i];
+            const unsigned long long mine = bndl[s * bcap + i];
             uint32_t rank = 0;
-            for (uint32_t j = 0; j < m; ++j) rank += bnd[s * kBoundaryCap + j] < mine ? 1u : 0u;
+            for (uint32_t j = 0; j < m; ++j) rank += bndl[s * bcap + j] < mine ? 1u : 0u;
             if (rank < need) {
                 const uint32_t slot = atomicAdd(s_nsel + s, 1u);
                 if (slot < (uint32_t)Ppad)
-                    sel[(size_t)s * Ppad + slot] = ((mine & 0xFFFFFFFFull) << 32) | bnd_pos[s * kBoundaryCap + i];
+                    sel[(size_t)s * Ppad + slot] = ((mine & 0xFFFFFFFFull) << 32) | bndp[s * bcap + i];
             }
         }
     }
@@ -516,7 +527,6 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
     while (ppad < P) ppad <<= 1;
     a.Ppad = ppad;
     a.cap = g_boundary_cap.load();
-    if (a.cap > kBoundaryCap) a.cap = kBoundaryCap;
     double rmax = 0.0;
     float hi_max = 0.f;
     for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
