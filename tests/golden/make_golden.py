@@ -15,6 +15,12 @@ half1_reference.npz  -- outputs of the reference's own
     traversal order); subsampled patches are stored as the reference produced
     them (only the subset property can be checked for those, the reference's
     draw comes from a stateful stream shared by all patches).
+half2_reference_numpy.npz -- outputs of the reference's own numpy code run
+    here: ``utils/utils.py::get_3d_grid_gmm`` (:70-95, the grid GMM fed to the
+    graph) and ``utils/utils.py::get_3DmFV`` (:260-330).  The latter differs
+    from the TF path in ONE stage (it takes Q = p, no posterior normalisation,
+    and has no mask), so it pins every other stage of the half-2 restatement
+    (``get_3dmfv_n_est(..., _posterior="pdf")``) against the reference itself.
 half2_oracle.npz -- inputs/outputs of the recorded fp32 transliteration of
     utils/tf_util.py:655-753 / :578-652 (TensorFlow 1.12 is not installable:
     PARITY UNPINNED), written only after the independent float64 restatement
@@ -160,6 +166,50 @@ def make_half2():
     np.savez_compressed(os.path.join(HERE, "half2_oracle.npz"), **out)
 
 
+def make_half2_reference_numpy():
+    """Run the reference's numpy get_3d_grid_gmm / get_3DmFV unmodified.  utils/utils.py imports the
+    reference's provider.py (h5py, absent here) and a private sklearn symbol that moved
+    (utils.py:93): both are satisfied with import shims, the reference code itself is untouched."""
+    import types
+    import sklearn.mixture._gaussian_mixture as skgm
+    sys.modules.setdefault("provider", types.ModuleType("provider"))
+    shim = types.ModuleType("sklearn.mixture.gaussian_mixture")
+    shim._compute_precision_cholesky = skgm._compute_precision_cholesky
+    sys.modules.setdefault("sklearn.mixture.gaussian_mixture", shim)
+    if REF_UTILS not in sys.path:
+        sys.path.insert(0, REF_UTILS)
+    import utils as ref_utils  # the unmodified reference module
+
+    rng = np.random.RandomState(23)
+    out = {}
+    for n, var in ((3, 0.11), (8, 0.0156), (16, 0.00390625)):
+        gmm = ref_utils.get_3d_grid_gmm(subdivisions=[n, n, n], variance=var)
+        out["grid%d_variance" % n] = np.float64(var)
+        out["grid%d_weights" % n] = np.asarray(gmm.weights_)
+        out["grid%d_means" % n] = np.asarray(gmm.means_)
+        out["grid%d_covariances" % n] = np.asarray(gmm.covariances_)
+    # (name, res, variance, B, P): points inside the unit ball like real patches; fp32 inputs
+    for name, res, var, B, P in (("g3", 3, 0.11, 5, 16), ("g8", 8, 0.0156, 4, 64), ("g8p512", 8, 0.0156, 2, 512)):
+        gmm = ref_utils.get_3d_grid_gmm(subdivisions=[res] * 3, variance=var)
+        # what the scripts feed the graph (train_n_est_w_experts.py:284-286)
+        w, mu, sigma = (np.asarray(gmm.weights_, np.float32), np.asarray(gmm.means_, np.float32),
+                        np.sqrt(gmm.covariances_).astype(np.float32))
+        x = rng.normal(size=(B, P, 3)) * 0.4
+        x /= np.maximum(1.0, np.linalg.norm(x, axis=2, keepdims=True))
+        x[:, 0] = 0.0
+        pts = x.astype(np.float32)
+        fv = ref_utils.get_3DmFV(pts, w, mu, sigma, normalize=True)           # [B, 20, G]
+        fv_raw = ref_utils.get_3DmFV(pts, w, mu, sigma, normalize=False)
+        mine = orc.get_3dmfv_n_est(pts, w, mu, sigma, flatten=False,
+                                   n_original_points=np.full(B, P, np.int32), _posterior="pdf")
+        print("half2 reference numpy case", name, fv.shape, "oracle(pdf hook) vs reference max abs err",
+              float(np.abs(mine - fv).max()))
+        out.update({name + "_points": pts, name + "_w": w, name + "_mu": mu, name + "_sigma": sigma,
+                    name + "_fv": np.asarray(fv, np.float64), name + "_fv_raw": np.asarray(fv_raw, np.float64)})
+    np.savez_compressed(os.path.join(HERE, "half2_reference_numpy.npz"), **out)
+
+
 if __name__ == "__main__":
     make_half1()
+    make_half2_reference_numpy()
     make_half2()

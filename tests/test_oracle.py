@@ -90,6 +90,47 @@ def test_philox_known_answers_and_c_port():
 
 # ---- half 2 ------------------------------------------------------------------------------------------
 
+@pytest.fixture(scope="module")
+def half2_ref(golden_dir):
+    return np.load(os.path.join(golden_dir, "half2_reference_numpy.npz"))
+
+
+@pytest.mark.parametrize("n", [3, 8, 16])
+def test_grid_gmm_matches_the_reference_run(half2_ref, n):
+    """utils/utils.py:70-95 run unmodified in the build container (make_golden.py): bit-identical arrays."""
+    w, mu, cov = orc.get_3d_grid_gmm([n] * 3, float(half2_ref["grid%d_variance" % n]))
+    assert np.array_equal(w, half2_ref["grid%d_weights" % n])
+    assert np.array_equal(mu, half2_ref["grid%d_means" % n])
+    assert np.array_equal(cov, half2_ref["grid%d_covariances" % n])
+
+
+@pytest.mark.parametrize("case", ["g3", "g8", "g8p512"])
+def test_half2_stages_pinned_by_reference_numpy(half2_ref, case):
+    """The reference's own numpy get_3DmFV (utils/utils.py:260-330), run unmodified, differs from the TF
+    path in one stage only (Q = p: no posterior normalisation, no mask).  With that stage switched off the
+    transliteration must reproduce the reference's outputs: prefactor, derivative terms, max/min/sum
+    reductions, 1/sqrt(w), 1/sqrt(2w), 1/n, signed square root, per-channel L2 norm, channel order."""
+    pts, w, mu, sg = (half2_ref["%s_%s" % (case, k)] for k in ("points", "w", "mu", "sigma"))
+    B, P, _ = pts.shape
+    ref = half2_ref[case + "_fv"]                                   # [B, 20, G] float64
+    got = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False, n_original_points=np.full(B, P, np.int32),
+                              _posterior="pdf")
+    assert got.shape == ref.shape
+    # the band, except where a sum channel is a near-complete fp32 cancellation (DESIGN.md 'Tolerance'): those
+    # few elements must be explained by <= 2e-7 of noise in the unit-norm statistic before the square root
+    bad = np.abs(got - ref) > TOL_ABS + TOL_REL * np.abs(ref)
+    assert bad.mean() <= 1e-4, (int(bad.sum()), np.abs(got - ref).max())
+    du = np.abs(got * np.abs(got) - ref * np.abs(ref))
+    assert not bad.any() or du[bad].max() <= 2e-7
+    assert np.abs(got - ref).max() < 5e-5
+    # flatten=True is the reference layout flattened channel-major (tf_util.py:743-748)
+    flat = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=True, n_original_points=np.full(B, P, np.int32),
+                               _posterior="pdf")
+    assert np.array_equal(flat, got.reshape(B, -1))
+    # and the default stays the posterior of tf_util.py:700-701 (rows of Q sum to one -> different numbers)
+    assert frac_outside(orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False,
+                                            n_original_points=np.full(B, P, np.int32)), ref) > 0.5
+
 @pytest.mark.parametrize("case", ["g3", "g8", "g8p512", "gen"])
 def test_half2_fixture_regression_and_c_port(half2, case):
     pts, ne, w, mu, sg = (half2["%s_%s" % (case, k)] for k in ("points", "n_eff", "w", "mu", "sigma"))
