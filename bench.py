@@ -422,7 +422,10 @@ def run_own(args):
 
     skip = set(os.environ.get("MUPS_BENCH_SKIP", "").split(","))      # profiling runs only: "e2e,cpu"
     # ---- end to end through the public API with host buffers ------------------------------------------
-    pipe = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=8192 if "e2e" not in skip else 64)
+    # chunk: query points per pipeline stage.  Small enough that the first device->host copy starts ~1.5 ms after the
+    # call (each cloud's call fills and drains the pipeline), large enough (336 MB per copy) for full PCIe rate.
+    chunk = int(os.environ.get("MUPS_BENCH_CHUNK", "2048"))
+    pipe = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=chunk if "e2e" not in skip else 64)
     hosts = [torch.from_numpy(c).pin_memory() for c in clouds_host]
     q_host = torch.arange(lo, hi, dtype=torch.int64).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
@@ -449,6 +452,7 @@ def run_own(args):
     barrier()
     e2e = {"value": n_done * n_gpus / float(e2e_s.item()), "unit": UNIT, "steps": e2e_steps,
            "h2d_bytes_per_step": pipe.h2d_bytes // e2e_steps, "d2h_bytes_per_step": pipe.d2h_bytes // e2e_steps,
+           "chunk_queries": pipe.chunk,
            "api": "MuPSPipeline.features_to_host (pinned host cloud in, MuPS rows streamed to pinned host memory)"}
 
     cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",

@@ -83,7 +83,7 @@ int mups_set_option(const char* name, int64_t value) {
         return MUPS_OK;
     }
     if (!strcmp(name, "stats_variant")) {
-        MUPS_REQUIRE(value >= 0 && value <= 16, "mups_set_option: stats_variant=%lld out of range", (long long)value);
+        MUPS_REQUIRE(value >= 0 && value <= 64, "mups_set_option: stats_variant=%lld out of range", (long long)value);
         g_stats_variant.store((int)value);
         return MUPS_OK;
     }

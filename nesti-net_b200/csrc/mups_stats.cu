@@ -351,12 +351,15 @@ __device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 
 // (query, scale).  CTA r owns task group r; the factor tables are staged once per cluster -- every CTA computes
 // 1/CL of the entries and writes them into all CL shared memories through distributed shared memory -- and the
 // per-channel sums of squares are exchanged the same way, so nothing is recomputed and nothing is re-read from HBM.
-template <int MINB, int MODE, int LOG_RES, int CL>
+template <int MINB, int MODE, int LOG_RES, int CL, int UNR = 1>
 __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(const StatsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TILE = CL > 1 ? kSepClusterTilePoints : kSepTilePoints;
     constexpr int NT = kSepThreads, TPP = TILE / 2;
-    constexpr bool PACKED_SUMS = MODE == 1;
+    constexpr int PM = MODE & 7;                 // product mode
+    constexpr bool PAIRSUM = (MODE & 8) != 0;    // sum += (lo + hi): the inner add reads an (even, odd) register pair,
+                                                 // so neither add has a register-bank conflict
+    constexpr bool PACKED_SUMS = PM == 1;
     constexpr int RES = 1 << LOG_RES;
     constexpr int nx = RES, ny = RES, nz = RES;
     float4* FA[3];
@@ -504,11 +507,11 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                 const float2* pxb = FB[0] + i;
                 const float2* pyb = FB[1] + j;
                 const float2* pzb = FB[2] + k0;
-#pragma unroll 1
+#pragma unroll UNR
                 for (int pp = 0; pp < npairs; ++pp, pxa += nx, pya += ny, pza += nz, pxb += nx, pyb += ny, pzb += nz) {
                     const float4 fx = *pxa, fy = *pya;
                     const float2 bx = *pxb, by = *pyb;
-                    if (MODE == 2) {
+                    if (PM == 2) {
                         // all scalar; products grouped so that consecutive multiplies share a source register
                         float u0[5], u1[5];      // qq, aq, qa, bq, qb of point 0 / point 1
                         u0[0] = fx.x * fy.x; u0[1] = fx.z * fy.x; u0[3] = bx.x * fy.x; u0[2] = fx.x * fy.z; u0[4] = fx.x * by.x;
@@ -524,9 +527,40 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                             v1[1] = u1[1] * fz.y; v1[2] = u1[2] * fz.y; v1[4] = u1[3] * fz.y; v1[5] = u1[4] * fz.y;
 #pragma unroll
                             for (int c = 0; c < 7; ++c) {
-                                ss[g][c] = (ss[g][c] + v0[c]) + v1[c];
+                                ss[g][c] = PAIRSUM ? ss[g][c] + (v0[c] + v1[c]) : (ss[g][c] + v0[c]) + v1[c];
                                 mx[g][c] = fmax3(mx[g][c], v0[c], v1[c]);
                                 if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], v0[c], v1[c]);
+                            }
+                        }
+                    } else if (PM == 3 || PM == 4) {
+                        // hybrid: the products that share u_qq (MODE 3: Q, Q t_z, Q (t_z^2-1); MODE 4: the last two)
+                        // as scalar FMUL, the rest packed -- balances FMA-pipe time against issue slots
+                        const u64 qx = pack2(fx.x, fx.y), ax_ = pack2(fx.z, fx.w), bx_ = pack2(bx.x, bx.y);
+                        const u64 qy = pack2(fy.x, fy.y), ay_ = pack2(fy.z, fy.w), by_ = pack2(by.x, by.y);
+                        const u64 u_aq = mul2(ax_, qy), u_qa = mul2(qx, ay_), u_bq = mul2(bx_, qy), u_qb = mul2(qx, by_);
+                        float q0, q1;
+                        u64 u_qq = 0ull;
+                        if (PM == 4) { u_qq = mul2(qx, qy); unpack2(u_qq, q0, q1); }
+                        else { q0 = fx.x * fy.x; q1 = fx.y * fy.y; }
+#pragma unroll
+                        for (int g = 0; g < kSepKPT; ++g) {
+                            const float4 fz = pza[g];
+                            const float2 bz = pzb[g];
+                            const u64 qz = pack2(fz.x, fz.y);
+                            float lo[7], hi[7];
+                            if (PM == 4) unpack2(mul2(u_qq, qz), lo[0], hi[0]);
+                            else { lo[0] = q0 * fz.x; hi[0] = q1 * fz.y; }
+                            unpack2(mul2(u_aq, qz), lo[1], hi[1]);
+                            unpack2(mul2(u_qa, qz), lo[2], hi[2]);
+                            lo[3] = q0 * fz.z; hi[3] = q1 * fz.w;
+                            unpack2(mul2(u_bq, qz), lo[4], hi[4]);
+                            unpack2(mul2(u_qb, qz), lo[5], hi[5]);
+                            lo[6] = q0 * bz.x; hi[6] = q1 * bz.y;
+#pragma unroll
+                            for (int c = 0; c < 7; ++c) {
+                                ss[g][c] = PAIRSUM ? ss[g][c] + (lo[c] + hi[c]) : (ss[g][c] + lo[c]) + hi[c];
+                                mx[g][c] = fmax3(mx[g][c], lo[c], hi[c]);
+                                if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo[c], hi[c]);
                             }
                         }
                     } else {
@@ -552,7 +586,7 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                                 float lo, hi;
                                 unpack2(t[c], lo, hi);
                                 if (PACKED_SUMS) sm[g][c] = add2(sm[g][c], t[c]);
-                                else ss[g][c] = (ss[g][c] + lo) + hi;
+                                else ss[g][c] = PAIRSUM ? ss[g][c] + (lo + hi) : (ss[g][c] + lo) + hi;
                                 mx[g][c] = fmax3(mx[g][c], lo, hi);
                                 if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo, hi);
                             }
@@ -701,12 +735,13 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
     const size_t smem = (size_t)TPP * (a.res[0] + a.res[1] + a.res[2]) * (sizeof(float4) + sizeof(float2)) +
                         sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
     const int variant = g_stats_variant.load();
-#define MUPS_LAUNCH_SEP(MINB, MODE, LOG)                                                                            \
+#define MUPS_LAUNCH_SEP_U(MINB, MODE, LOG, UNR)                                                                     \
     do {                                                                                                            \
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, MODE, LOG, 1>,                              \
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, MODE, LOG, 1, UNR>,                         \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-        stats_separable_kernel<MINB, MODE, LOG, 1><<<(unsigned)items, kSepThreads, smem, st>>>(a);                  \
+        stats_separable_kernel<MINB, MODE, LOG, 1, UNR><<<(unsigned)items, kSepThreads, smem, st>>>(a);             \
     } while (0)
+#define MUPS_LAUNCH_SEP(MINB, MODE, LOG) MUPS_LAUNCH_SEP_U(MINB, MODE, LOG, 1)
 #define MUPS_LAUNCH_SEP_RES(MINB, MODE)                                                                             \
     do {                                                                                                            \
         if (a.shift[0] == 2) MUPS_LAUNCH_SEP(MINB, MODE, 2);                                                        \
@@ -739,9 +774,21 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
     else if (variant == 5) MUPS_LAUNCH_SEP_RES(3, 0);
     else if (variant == 6) MUPS_LAUNCH_SEP_RES(4, 2);
     else if (variant == 7) MUPS_LAUNCH_SEP_RES(3, 2);
-    else MUPS_LAUNCH_SEP_RES(4, 0);
+    else if (variant == 9 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 3, 3, 1);
+    else if (variant == 10 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 4, 3, 1);
+    else if (variant == 11 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 0, 3, 2);
+    else if (variant == 12 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 3, 3, 2);
+    else if (variant == 13 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 4, 3, 2);
+    else if (variant == 14 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 8, 3, 1);
+    else if (variant == 15 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 10, 3, 1);
+    else if (variant == 16 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 12, 3, 1);
+    else if (variant == 17 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 11, 3, 1);
+    else if (variant == 18 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 8, 3, 2);
+    else if (variant == 1) MUPS_LAUNCH_SEP_RES(4, 0);
+    else MUPS_LAUNCH_SEP_RES(4, 12);      // default: hybrid packed/scalar products, pairwise sums
 #undef MUPS_LAUNCH_SEP_RES
 #undef MUPS_LAUNCH_SEP
+#undef MUPS_LAUNCH_SEP_U
     MUPS_CHECK_LAUNCH();
     // patches that left the lattice's 5-sigma box (none for real patches, which live in the unit ball)
     a.use_worklist = 1;

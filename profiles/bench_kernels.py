@@ -58,7 +58,14 @@ def main():
     reps = int(os.environ.get("REPS", 2))
     for rep in range(reps):
         for name, variant, fast in (("general", 0, False), ("sep_minb4_scalar", 0, True), ("sep_minb3_scalar", 5, True),
-                                    ("sep_minb3_packed", 3, True), ("sep_minb4_allscalar", 6, True), ("sep_minb3_allscalar", 7, True)):
+                                    ("sep_minb3_packed", 3, True), ("sep_minb4_allscalar", 6, True), ("sep_minb3_allscalar", 7, True),
+                                    ("sep_hybrid_qq_scalar", 9, True), ("sep_hybrid_tz_scalar", 10, True),
+                                    ("sep_packed_unroll2", 11, True), ("sep_hybrid_qq_unroll2", 12, True),
+                                    ("sep_hybrid_tz_unroll2", 13, True), ("sep_packed_pairsum", 14, True),
+                                    ("sep_allscalar_pairsum", 15, True), ("sep_hybrid_tz_pairsum", 16, True),
+                                    ("sep_hybrid_qq_pairsum", 17, True), ("sep_packed_pairsum_unroll2", 18, True)):
+            if os.environ.get("ONLY") and str(variant) not in os.environ["ONLY"].split(",") :
+                continue
             if rep and name == "general":
                 continue
             _lib.set_option("stats_variant", variant)
