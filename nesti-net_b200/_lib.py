@@ -79,6 +79,9 @@ def load():
     if L.mups_abi_version() != 1:
         raise RuntimeError("libmups_b200.so ABI version %d, expected 1" % L.mups_abi_version())
     _lib = L
+    v = os.environ.get("MUPS_STATS_VARIANT")        # benchmarking / A-B testing only (see mups_set_option)
+    if v:
+        L.mups_set_option(b"stats_variant", int(v))
     return L
 
 

@@ -49,6 +49,7 @@ struct StatsArgs {
     int* worklist;             // [B*S] item ids
     int* work_count;           // [1]
     int use_worklist;          // general kernel: take items from the worklist
+    int gmm_in_smem;           // general kernel: stage A / Bv in shared memory (else read them through L1/L2)
 };
 
 typedef unsigned long long u64;
@@ -79,11 +80,6 @@ __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     u64 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 
@@ -180,16 +176,18 @@ template <int GPT, int NT>
 __global__ void __launch_bounds__(NT) stats_general_kernel(const StatsArgs a) {
     extern __shared__ __align__(16) float4 smem4[];
     const int G = a.G, S = a.S, P = a.P;
-    float4* gA = smem4;
-    float4* gB = gA + G;
-    float4* pt = gB + G;
+    // the Gaussians are staged in shared memory when they fit (G <= ~6500); very fine lattices read them through L1
+    const float4* gA = a.gmm_in_smem ? smem4 : a.A;
+    const float4* gB = a.gmm_in_smem ? smem4 + G : a.Bv;
+    float4* pt = smem4 + (a.gmm_in_smem ? 2 * G : 0);
     float* part = reinterpret_cast<float*>(pt + P);       // [max(NT, P)]
     float* red = part + (NT > P ? NT : P);                // [NT/32][20]
     float* inv_norm = red + (NT / 32) * 20;               // [20]
 
     const int tid = threadIdx.x;
     const bool masked = (a.flags & MUPS_FLAG_MASKED) != 0;
-    for (int i = tid; i < G; i += NT) { gA[i] = __ldg(a.A + i); gB[i] = __ldg(a.Bv + i); }
+    if (a.gmm_in_smem)
+        for (int i = tid; i < G; i += NT) { smem4[i] = __ldg(a.A + i); smem4[G + i] = __ldg(a.Bv + i); }
 
     const int n_items = a.use_worklist ? *a.work_count : (int)gridDim.x;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -326,6 +324,7 @@ __global__ void __launch_bounds__(NT) stats_general_kernel(const StatsArgs a) {
 // =====================================================================================================
 
 constexpr int kSepThreads = 128;
+constexpr int kSepMinBlocks = 4;        // 128 registers per thread: 80 running reductions + operands; 4 CTAs per SM
 constexpr int kSepKPT = 4;              // Gaussians per thread, consecutive along z
 constexpr int kSepTilePoints = 128;     // points staged per tile (64 point pairs)
 constexpr int kSepClusterTilePoints = 64;   // cluster variant: smaller tiles keep 4 CTAs per SM at 16^3
@@ -344,33 +343,40 @@ __device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 
 // (<= 8 distinct j, <= 4 distinct i, one k-quad) are bank-conflict free.
 // LOG_RES: the lattice is RES x RES x RES with RES = 1 << LOG_RES in {4, 8, 16, 32} (get_3d_grid_gmm is always
 // called with [n, n, n]); other lattices take the general kernel.
-// MODE 0: packed FMUL2 products + scalar sums; 1: packed products + packed sums; 2: all scalar (more
-// instructions, but none that needs four distinct source registers)
+// MODE: how the 7 products per (point, Gaussian) and their sums are issued (all variants measured within 5 % of
+// each other: the loop is bound by operand delivery / dispatch, not by one pipe -- profiles/README.md):
+//   0  packed FMUL2 products, sums as (s + lo) + hi
+//   1  hybrid: Q t_z and Q (t_z^2 - 1) as scalar FMUL, the other five packed; sums as s + (lo + hi) -- the inner add
+//      reads an (even, odd) register pair, so neither add has a register-bank conflict.  Default.
+//   2  all products scalar, pairwise sums
 //
 // CL > 1 (16^3 lattice: 1024 thread-tasks = 8 groups of 128): a thread-block CLUSTER of CL CTAs shares one
 // (query, scale).  CTA r owns task group r; the factor tables are staged once per cluster -- every CTA computes
 // 1/CL of the entries and writes them into all CL shared memories through distributed shared memory -- and the
 // per-channel sums of squares are exchanged the same way, so nothing is recomputed and nothing is re-read from HBM.
-template <int MINB, int MODE, int LOG_RES, int CL, int UNR = 1>
-__global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(const StatsArgs a) {
+// STG 1 (small lattices, no cluster): the staging lane-task is one (point pair, axis) and walks the lattice axis
+// serially -- no shuffle reductions, ~1/3 fewer instructions and much shorter dependency chains than one lane per
+// (pair, axis, lattice index); table rows are padded to RES + 1 entries so that these strided writers stay
+// bank-conflict free (the readers touch one row per step and do not care).
+template <int MODE, int LOG_RES, int CL, int STG>
+__global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_kernel(const StatsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TILE = CL > 1 ? kSepClusterTilePoints : kSepTilePoints;
     constexpr int NT = kSepThreads, TPP = TILE / 2;
-    constexpr int PM = MODE & 7;                 // product mode
-    constexpr bool PAIRSUM = (MODE & 8) != 0;    // sum += (lo + hi): the inner add reads an (even, odd) register pair,
-                                                 // so neither add has a register-bank conflict
-    constexpr bool PACKED_SUMS = PM == 1;
+    constexpr bool PAIRSUM = MODE != 0;
     constexpr int RES = 1 << LOG_RES;
     constexpr int nx = RES, ny = RES, nz = RES;
+    static_assert(STG == 0 || (CL == 1 && RES <= 8), "serial staging: small lattices, single CTA");
+    constexpr int PITCH = STG ? RES + 1 : RES;   // entries per (axis, point pair) table row
     float4* FA[3];
     float2* FB[3];
     FA[0] = reinterpret_cast<float4*>(smem_raw);
-    FA[1] = FA[0] + TPP * nx;
-    FA[2] = FA[1] + TPP * ny;
-    FB[0] = reinterpret_cast<float2*>(FA[2] + TPP * nz);
-    FB[1] = FB[0] + TPP * nx;
-    FB[2] = FB[1] + TPP * ny;
-    float* lat = reinterpret_cast<float*>(FB[2] + TPP * nz);   // [3][64] lattice coordinates
+    FA[1] = FA[0] + TPP * PITCH;
+    FA[2] = FA[1] + TPP * PITCH;
+    FB[0] = reinterpret_cast<float2*>(FA[2] + TPP * PITCH);
+    FB[1] = FB[0] + TPP * PITCH;
+    FB[2] = FB[1] + TPP * PITCH;
+    float* lat = reinterpret_cast<float*>(FB[2] + TPP * PITCH);   // [3][64] lattice coordinates
     float* red = lat + 3 * 64;                                 // [NT/32][20]
     float* inv_norm = red + (NT / 32) * 20;                    // [20] (+12 pad)
     float* axis_par = inv_norm + 20;                           // [3][4]: 1/sigma, guard lo, guard hi
@@ -425,13 +431,11 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
         const int j = tk % ny, i = (tk / ny) % nx, kq = tk / nxy;
         const int k0 = kq * kSepKPT;
 
-        u64 sm[kSepKPT][7];       // packed (even point, odd point) partial sums
-        float ss[kSepKPT][7];     // or scalar sums (fewer registers: one more CTA per SM)
-        float mx[kSepKPT][7], mn[kSepKPT][6];
+        float ss[kSepKPT][7], mx[kSepKPT][7], mn[kSepKPT][6];     // 28 sums, 28 max, 24 min
 #pragma unroll
         for (int g = 0; g < kSepKPT; ++g) {
 #pragma unroll
-            for (int c = 0; c < 7; ++c) { sm[g][c] = 0ull; ss[g][c] = 0.f; mx[g][c] = -INFINITY; }
+            for (int c = 0; c < 7; ++c) { ss[g][c] = 0.f; mx[g][c] = -INFINITY; }
 #pragma unroll
             for (int c = 0; c < 6; ++c) mn[g][c] = INFINITY;
         }
@@ -439,6 +443,54 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
         for (int tile0 = 0; tile0 < m; tile0 += TILE) {
             const int tile_pts = min(TILE, m - tile0);
             const int npairs = (tile_pts + 1) >> 1;
+            if (STG) {
+                // ---- stage the per-axis factors of this tile: one lane per (point pair, axis) ----
+                const int total = 3 * npairs;
+                const float* ctile = coords + 3 * tile0;
+                const int last = tile_pts - 1;                                     // last real point of the tile
+                bool bad = false;
+                for (int t = tid; t < total; t += NT) {
+                    const int ax = (t >= npairs) + (t >= 2 * npairs);              // axis-major: a warp's lanes share the axis
+                    const int pp = t - ax * npairs;
+                    const bool real1 = 2 * pp + 1 <= last;                          // the odd tail has no second point
+                    const float c0 = ctile[6 * pp + ax];
+                    const float c1 = ctile[3 * min(2 * pp + 1, last) + ax];
+                    const float isg = axis_par[4 * ax];
+                    const float4* lat4 = reinterpret_cast<const float4*>(lat + ax * 64);
+                    float4* fa = FA[0] + ax * (TPP * PITCH) + pp * PITCH;
+                    float2* fb = FB[0] + ax * (TPP * PITCH) + pp * PITCH;
+                    // pass 1: unnormalised factors and t parked in the table row itself (keeps the register
+                    // footprint of this phase small: the 80 running reductions stay live across it)
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int v = 0; v < RES / 4; ++v) {
+                        const float4 m4 = lat4[v];
+                        const float mu4[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float t0 = (c0 - mu4[u]) * isg, t1 = (c1 - mu4[u]) * isg;
+                            const float e0 = ex2_approx(kNegHalfLog2e * t0 * t0), e1 = ex2_approx(kNegHalfLog2e * t1 * t1);
+                            s0 += e0;
+                            s1 += e1;
+                            fa[4 * v + u] = make_float4(e0, e1, t0, t1);
+                        }
+                    }
+                    const float r0 = __fdividef(1.0f, s0);
+                    const float r1 = real1 ? __fdividef(1.0f, s1) : 0.f;            // a missing second point contributes exact zeros
+                    // pass 2: normalise, q t and q (t^2 - 1)
+#pragma unroll
+                    for (int li = 0; li < RES; ++li) {
+                        const float4 f = fa[li];
+                        const float q0 = f.x * r0, q1 = f.y * r1;
+                        const float a0 = q0 * f.z, a1 = q1 * f.w;
+                        fa[li] = make_float4(q0, q1, a0, a1);
+                        fb[li] = make_float2(fmaf(a0, f.z, -q0), fmaf(a1, f.w, -q1));
+                    }
+                    const float glo = axis_par[4 * ax + 1], ghi = axis_par[4 * ax + 2];
+                    bad |= !(c0 >= glo && c0 <= ghi) || !(c1 >= glo && c1 <= ghi);   // outside the 5-sigma box (or NaN)
+                }
+                if (bad) s_fallback = 1;
+            } else
             // ---- stage the per-axis factors of this tile: one lane per (point pair, axis, lattice index) ----
             {
                 const int total = (npairs * 3) << LOG_RES;
@@ -507,11 +559,11 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                 const float2* pxb = FB[0] + i;
                 const float2* pyb = FB[1] + j;
                 const float2* pzb = FB[2] + k0;
-#pragma unroll UNR
-                for (int pp = 0; pp < npairs; ++pp, pxa += nx, pya += ny, pza += nz, pxb += nx, pyb += ny, pzb += nz) {
+#pragma unroll 1
+                for (int pp = 0; pp < npairs; ++pp, pxa += PITCH, pya += PITCH, pza += PITCH, pxb += PITCH, pyb += PITCH, pzb += PITCH) {
                     const float4 fx = *pxa, fy = *pya;
                     const float2 bx = *pxb, by = *pyb;
-                    if (PM == 2) {
+                    if (MODE == 2) {
                         // all scalar; products grouped so that consecutive multiplies share a source register
                         float u0[5], u1[5];      // qq, aq, qa, bq, qb of point 0 / point 1
                         u0[0] = fx.x * fy.x; u0[1] = fx.z * fy.x; u0[3] = bx.x * fy.x; u0[2] = fx.x * fy.z; u0[4] = fx.x * by.x;
@@ -520,45 +572,14 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                         for (int g = 0; g < kSepKPT; ++g) {
                             const float4 fz = pza[g];
                             const float2 bz = pzb[g];
-                            float v0[7], v1[7];
-                            v0[0] = u0[0] * fz.x; v0[3] = u0[0] * fz.z; v0[6] = u0[0] * bz.x;
-                            v0[1] = u0[1] * fz.x; v0[2] = u0[2] * fz.x; v0[4] = u0[3] * fz.x; v0[5] = u0[4] * fz.x;
-                            v1[0] = u1[0] * fz.y; v1[3] = u1[0] * fz.w; v1[6] = u1[0] * bz.y;
-                            v1[1] = u1[1] * fz.y; v1[2] = u1[2] * fz.y; v1[4] = u1[3] * fz.y; v1[5] = u1[4] * fz.y;
-#pragma unroll
-                            for (int c = 0; c < 7; ++c) {
-                                ss[g][c] = PAIRSUM ? ss[g][c] + (v0[c] + v1[c]) : (ss[g][c] + v0[c]) + v1[c];
-                                mx[g][c] = fmax3(mx[g][c], v0[c], v1[c]);
-                                if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], v0[c], v1[c]);
-                            }
-                        }
-                    } else if (PM == 3 || PM == 4) {
-                        // hybrid: the products that share u_qq (MODE 3: Q, Q t_z, Q (t_z^2-1); MODE 4: the last two)
-                        // as scalar FMUL, the rest packed -- balances FMA-pipe time against issue slots
-                        const u64 qx = pack2(fx.x, fx.y), ax_ = pack2(fx.z, fx.w), bx_ = pack2(bx.x, bx.y);
-                        const u64 qy = pack2(fy.x, fy.y), ay_ = pack2(fy.z, fy.w), by_ = pack2(by.x, by.y);
-                        const u64 u_aq = mul2(ax_, qy), u_qa = mul2(qx, ay_), u_bq = mul2(bx_, qy), u_qb = mul2(qx, by_);
-                        float q0, q1;
-                        u64 u_qq = 0ull;
-                        if (PM == 4) { u_qq = mul2(qx, qy); unpack2(u_qq, q0, q1); }
-                        else { q0 = fx.x * fy.x; q1 = fx.y * fy.y; }
-#pragma unroll
-                        for (int g = 0; g < kSepKPT; ++g) {
-                            const float4 fz = pza[g];
-                            const float2 bz = pzb[g];
-                            const u64 qz = pack2(fz.x, fz.y);
                             float lo[7], hi[7];
-                            if (PM == 4) unpack2(mul2(u_qq, qz), lo[0], hi[0]);
-                            else { lo[0] = q0 * fz.x; hi[0] = q1 * fz.y; }
-                            unpack2(mul2(u_aq, qz), lo[1], hi[1]);
-                            unpack2(mul2(u_qa, qz), lo[2], hi[2]);
-                            lo[3] = q0 * fz.z; hi[3] = q1 * fz.w;
-                            unpack2(mul2(u_bq, qz), lo[4], hi[4]);
-                            unpack2(mul2(u_qb, qz), lo[5], hi[5]);
-                            lo[6] = q0 * bz.x; hi[6] = q1 * bz.y;
+                            lo[0] = u0[0] * fz.x; lo[3] = u0[0] * fz.z; lo[6] = u0[0] * bz.x;
+                            lo[1] = u0[1] * fz.x; lo[2] = u0[2] * fz.x; lo[4] = u0[3] * fz.x; lo[5] = u0[4] * fz.x;
+                            hi[0] = u1[0] * fz.y; hi[3] = u1[0] * fz.w; hi[6] = u1[0] * bz.y;
+                            hi[1] = u1[1] * fz.y; hi[2] = u1[2] * fz.y; hi[4] = u1[3] * fz.y; hi[5] = u1[4] * fz.y;
 #pragma unroll
                             for (int c = 0; c < 7; ++c) {
-                                ss[g][c] = PAIRSUM ? ss[g][c] + (lo[c] + hi[c]) : (ss[g][c] + lo[c]) + hi[c];
+                                ss[g][c] += lo[c] + hi[c];
                                 mx[g][c] = fmax3(mx[g][c], lo[c], hi[c]);
                                 if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo[c], hi[c]);
                             }
@@ -568,27 +589,31 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
                         const u64 qy = pack2(fy.x, fy.y), ay_ = pack2(fy.z, fy.w), by_ = pack2(by.x, by.y);
                         const u64 u_qq = mul2(qx, qy), u_aq = mul2(ax_, qy), u_qa = mul2(qx, ay_), u_bq = mul2(bx_, qy),
                                   u_qb = mul2(qx, by_);
+                        float q0, q1;
+                        unpack2(u_qq, q0, q1);
 #pragma unroll
                         for (int g = 0; g < kSepKPT; ++g) {
                             const float4 fz = pza[g];
                             const float2 bz = pzb[g];
-                            const u64 qz = pack2(fz.x, fz.y), az_ = pack2(fz.z, fz.w), bz_ = pack2(bz.x, bz.y);
-                            u64 t[7];
-                            t[0] = mul2(u_qq, qz);     // Q
-                            t[1] = mul2(u_aq, qz);     // Q t_x
-                            t[2] = mul2(u_qa, qz);     // Q t_y
-                            t[3] = mul2(u_qq, az_);    // Q t_z
-                            t[4] = mul2(u_bq, qz);     // Q (t_x^2 - 1)
-                            t[5] = mul2(u_qb, qz);     // Q (t_y^2 - 1)
-                            t[6] = mul2(u_qq, bz_);    // Q (t_z^2 - 1)
+                            const u64 qz = pack2(fz.x, fz.y);
+                            float lo[7], hi[7];
+                            unpack2(mul2(u_qq, qz), lo[0], hi[0]);     // Q
+                            unpack2(mul2(u_aq, qz), lo[1], hi[1]);     // Q t_x
+                            unpack2(mul2(u_qa, qz), lo[2], hi[2]);     // Q t_y
+                            unpack2(mul2(u_bq, qz), lo[4], hi[4]);     // Q (t_x^2 - 1)
+                            unpack2(mul2(u_qb, qz), lo[5], hi[5]);     // Q (t_y^2 - 1)
+                            if (MODE == 1) {
+                                lo[3] = q0 * fz.z; hi[3] = q1 * fz.w;  // Q t_z
+                                lo[6] = q0 * bz.x; hi[6] = q1 * bz.y;  // Q (t_z^2 - 1)
+                            } else {
+                                unpack2(mul2(u_qq, pack2(fz.z, fz.w)), lo[3], hi[3]);
+                                unpack2(mul2(u_qq, pack2(bz.x, bz.y)), lo[6], hi[6]);
+                            }
 #pragma unroll
                             for (int c = 0; c < 7; ++c) {
-                                float lo, hi;
-                                unpack2(t[c], lo, hi);
-                                if (PACKED_SUMS) sm[g][c] = add2(sm[g][c], t[c]);
-                                else ss[g][c] = PAIRSUM ? ss[g][c] + (lo + hi) : (ss[g][c] + lo) + hi;
-                                mx[g][c] = fmax3(mx[g][c], lo, hi);
-                                if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo, hi);
+                                ss[g][c] = PAIRSUM ? ss[g][c] + (lo[c] + hi[c]) : (ss[g][c] + lo[c]) + hi[c];
+                                mx[g][c] = fmax3(mx[g][c], lo[c], hi[c]);
+                                if (c > 0) mn[g][c - 1] = fmin3(mn[g][c - 1], lo[c], hi[c]);
                             }
                         }
                     }
@@ -601,13 +626,7 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
         // ---- per-Gaussian epilogue (same steps as finalize_gaussian, with fast reciprocal/sqrt) -------------
 #pragma unroll
         for (int g = 0; g < kSepKPT; ++g) {
-            float sums[7];
-#pragma unroll
-            for (int c = 0; c < 7; ++c) {
-                float lo, hi;
-                unpack2(sm[g][c], lo, hi);
-                sums[c] = PACKED_SUMS ? lo + hi : ss[g][c];
-            }
+            const float* sums = ss[g];
             // d_pi = (Q - w)/sqrt(w): max and sum over the m unmasked slots (tf_util.py:710-712)
             v[g][0] = (mx[g][0] - w) * pis;
             v[g][1] = fmaf(-(float)m, w, sums[0]) * pis;
@@ -681,8 +700,11 @@ __global__ void __launch_bounds__(kSepThreads, MINB) stats_separable_kernel(cons
 // =====================================================================================================
 
 template <int GPT, int NT>
-static int launch_general(const StatsArgs& a, int64_t items, int grid, cudaStream_t st) {
-    const size_t smem = sizeof(float4) * (2 * (size_t)a.G + a.P) + sizeof(float) * ((NT > a.P ? NT : a.P) + (NT / 32) * 20 + 32);
+static int launch_general(const StatsArgs& a_in, int64_t items, int grid, cudaStream_t st) {
+    StatsArgs a = a_in;
+    const size_t rest = sizeof(float4) * (size_t)a.P + sizeof(float) * ((NT > a.P ? NT : a.P) + (NT / 32) * 20 + 32);
+    a.gmm_in_smem = sizeof(float4) * 2 * (size_t)a.G + rest <= 200 * 1024;
+    const size_t smem = rest + (a.gmm_in_smem ? sizeof(float4) * 2 * (size_t)a.G : 0);
     if (smem > 220 * 1024) {
         set_error("3dmfv: G=%d, P=%d needs %zu bytes of shared memory", a.G, a.P, smem);
         return MUPS_ERR_UNSUPPORTED;
@@ -716,7 +738,7 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
         while ((1 << a.shift[k]) < a.res[k]) ++a.shift[k];
     }
     a.w_uniform = gmm->w_uniform;
-    a.worklist = nullptr; a.work_count = nullptr; a.use_worklist = 0;
+    a.worklist = nullptr; a.work_count = nullptr; a.use_worklist = 0; a.gmm_in_smem = 1;
     if (B == 0) return MUPS_OK;
     const int64_t items = B * (int64_t)S;
     if (items > 0x7FFFFFFFll) {
@@ -731,28 +753,12 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
     a.work_count = work;
     a.worklist = work + 1;
     MUPS_CUDA_TRY(cudaMemsetAsync(work, 0, sizeof(int), st));
-    const int TPP = kSepTilePoints / 2;
-    const size_t smem = (size_t)TPP * (a.res[0] + a.res[1] + a.res[2]) * (sizeof(float4) + sizeof(float2)) +
-                        sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
-    const int variant = g_stats_variant.load();
-#define MUPS_LAUNCH_SEP_U(MINB, MODE, LOG, UNR)                                                                     \
-    do {                                                                                                            \
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MINB, MODE, LOG, 1, UNR>,                         \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-        stats_separable_kernel<MINB, MODE, LOG, 1, UNR><<<(unsigned)items, kSepThreads, smem, st>>>(a);             \
-    } while (0)
-#define MUPS_LAUNCH_SEP(MINB, MODE, LOG) MUPS_LAUNCH_SEP_U(MINB, MODE, LOG, 1)
-#define MUPS_LAUNCH_SEP_RES(MINB, MODE)                                                                             \
-    do {                                                                                                            \
-        if (a.shift[0] == 2) MUPS_LAUNCH_SEP(MINB, MODE, 2);                                                        \
-        else if (a.shift[0] == 3) MUPS_LAUNCH_SEP(MINB, MODE, 3);                                                   \
-        else if (a.shift[0] == 4) MUPS_LAUNCH_SEP(MINB, MODE, 4);                                                   \
-        else MUPS_LAUNCH_SEP(MINB, MODE, 5);                                                                        \
-    } while (0)
-    if (a.shift[0] == 4 && variant != 8 && items * 8 <= 0x7FFFFFFFll) {
+    const int variant = g_stats_variant.load();      // 0 automatic; 1 round-1 loop; 2 all-scalar loop; 8 no cluster at 16^3
+    const int log_res = a.shift[0];
+    if (log_res == 4 && variant != 8 && items * 8 <= 0x7FFFFFFFll) {
         // 16^3 lattice: one thread-block cluster of 8 CTAs per (query, scale), tables shared through DSMEM
         constexpr int kCl = 8;
-        auto kern = stats_separable_kernel<4, 0, 4, kCl>;
+        auto kern = stats_separable_kernel<0, 4, kCl, 0>;
         const size_t smem_cl = (size_t)(kSepClusterTilePoints / 2) * 3 * 16 * (sizeof(float4) + sizeof(float2)) +
                                sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P + kCl * 20);
         MUPS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));
@@ -769,26 +775,31 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         MUPS_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
-    } else if (variant == 2) MUPS_LAUNCH_SEP_RES(2, 1);
-    else if (variant == 3) MUPS_LAUNCH_SEP_RES(3, 1);
-    else if (variant == 5) MUPS_LAUNCH_SEP_RES(3, 0);
-    else if (variant == 6) MUPS_LAUNCH_SEP_RES(4, 2);
-    else if (variant == 7) MUPS_LAUNCH_SEP_RES(3, 2);
-    else if (variant == 9 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 3, 3, 1);
-    else if (variant == 10 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 4, 3, 1);
-    else if (variant == 11 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 0, 3, 2);
-    else if (variant == 12 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 3, 3, 2);
-    else if (variant == 13 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 4, 3, 2);
-    else if (variant == 14 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 8, 3, 1);
-    else if (variant == 15 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 10, 3, 1);
-    else if (variant == 16 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 12, 3, 1);
-    else if (variant == 17 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 11, 3, 1);
-    else if (variant == 18 && a.shift[0] == 3) MUPS_LAUNCH_SEP_U(4, 8, 3, 2);
-    else if (variant == 1) MUPS_LAUNCH_SEP_RES(4, 0);
-    else MUPS_LAUNCH_SEP_RES(4, 12);      // default: hybrid packed/scalar products, pairwise sums
-#undef MUPS_LAUNCH_SEP_RES
+    } else {
+        // one CTA per (query, scale); res <= 8: serial staging with padded table rows (pitch res + 1)
+        const int TPP = kSepTilePoints / 2;
+        const bool serial = log_res <= 3 && variant != 1;
+        const int pitch = a.res[0] + (serial ? 1 : 0);
+        const size_t smem = (size_t)TPP * 3 * pitch * (sizeof(float4) + sizeof(float2)) +
+                            sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
+#define MUPS_LAUNCH_SEP(MODE, LOG, STG)                                                                             \
+    do {                                                                                                            \
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MODE, LOG, 1, STG>,                               \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+        stats_separable_kernel<MODE, LOG, 1, STG><<<(unsigned)items, kSepThreads, smem, st>>>(a);                   \
+    } while (0)
+        if (variant == 1) {                      // the round-1 kernel: packed products, sequential sums, shuffle staging
+            if (log_res == 2) MUPS_LAUNCH_SEP(0, 2, 0);
+            else if (log_res == 3) MUPS_LAUNCH_SEP(0, 3, 0);
+            else if (log_res == 4) MUPS_LAUNCH_SEP(0, 4, 0);
+            else MUPS_LAUNCH_SEP(0, 5, 0);
+        } else if (variant == 2 && log_res == 3) MUPS_LAUNCH_SEP(2, 3, 1);
+        else if (log_res == 2) MUPS_LAUNCH_SEP(1, 2, 1);
+        else if (log_res == 3) MUPS_LAUNCH_SEP(1, 3, 1);
+        else if (log_res == 4) MUPS_LAUNCH_SEP(1, 4, 0);
+        else MUPS_LAUNCH_SEP(1, 5, 0);
 #undef MUPS_LAUNCH_SEP
-#undef MUPS_LAUNCH_SEP_U
+    }
     MUPS_CHECK_LAUNCH();
     // patches that left the lattice's 5-sigma box (none for real patches, which live in the unit ball)
     a.use_worklist = 1;

@@ -57,16 +57,11 @@ def main():
                       "mean_unmasked_points_per_query": float(m.sum()) / nq, "pairs_per_query": pairs / nq}))
     reps = int(os.environ.get("REPS", 2))
     for rep in range(reps):
-        for name, variant, fast in (("general", 0, False), ("sep_minb4_scalar", 0, True), ("sep_minb3_scalar", 5, True),
-                                    ("sep_minb3_packed", 3, True), ("sep_minb4_allscalar", 6, True), ("sep_minb3_allscalar", 7, True),
-                                    ("sep_hybrid_qq_scalar", 9, True), ("sep_hybrid_tz_scalar", 10, True),
-                                    ("sep_packed_unroll2", 11, True), ("sep_hybrid_qq_unroll2", 12, True),
-                                    ("sep_hybrid_tz_unroll2", 13, True), ("sep_packed_pairsum", 14, True),
-                                    ("sep_allscalar_pairsum", 15, True), ("sep_hybrid_tz_pairsum", 16, True),
-                                    ("sep_hybrid_qq_pairsum", 17, True), ("sep_packed_pairsum_unroll2", 18, True)):
-            if os.environ.get("ONLY") and str(variant) not in os.environ["ONLY"].split(",") :
-                continue
+        for name, variant, fast in (("general", 0, False), ("sep_default_hybrid_pairsum_serialstage", 0, True),
+                                    ("sep_round1_packed_shufflestage", 1, True), ("sep_allscalar_pairsum_serialstage", 2, True)):
             if rep and name == "general":
+                continue
+            if os.environ.get("ONLY") and str(variant) not in os.environ["ONLY"].split(","):
                 continue
             _lib.set_option("stats_variant", variant)
             t = timed(lambda: mb.stats_3dmfv(patches, n_eff, gmm, S, out=feats, fastpath=fast), iters=10, warm=3)

@@ -2,7 +2,7 @@
 """Summarise one kernel of an .ncu-rep (captured with --set full --import-source on) as markdown:
 key counters (duration, DRAM bytes, pipe utilisation, stall reasons, occupancy limits) plus the
 instruction/stall share of the code regions between barriers.
-usage: summarize_ncu.py <rep> <title> [queries-per-launch] > profiles/rNN_<kernel>.md"""
+usage: summarize_ncu.py <rep> <title> [queries-per-launch] [kernel-name-regex] > profiles/rNN_<kernel>.md"""
 import csv
 import io
 import subprocess
@@ -24,14 +24,20 @@ KEYS = [
 ]
 
 
+KERNEL = None
+
+
 def page(rep, name):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", name, "--csv"] + (["-k", "regex:" + KERNEL] if KERNEL else [])
+    txt = subprocess.run(cmd, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(txt)))
 
 
 def main():
     rep, title = sys.argv[1], sys.argv[2]
     nq = float(sys.argv[3]) if len(sys.argv) > 3 else None
+    global KERNEL
+    KERNEL = sys.argv[4] if len(sys.argv) > 4 else None
     raw = page(rep, "raw")
     hdr, units, vals = raw[0], raw[1], raw[2]
     m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}

@@ -259,7 +259,8 @@ def test_half2_reference_signatures(half2):
 
 @pytest.mark.parametrize("fastpath", [True, False])
 @pytest.mark.parametrize("res,P,S,var", [(8, 512, 4, 0.0156), (8, 512, 3, 0.0156), (3, 64, 2, 0.11), (5, 100, 1, 0.04),
-                                         (8, 256, 4, 0.0156), (8, 1024, 2, 0.0156), (16, 128, 2, 0.00390625)])
+                                         (8, 256, 4, 0.0156), (8, 1024, 2, 0.0156), (16, 128, 2, 0.00390625),
+                                         (4, 96, 2, 0.0625), (8, 130, 1, 0.0156), (32, 32, 1, 0.0009765625)])
 def test_half2_mups_layout_against_oracle(res, P, S, var, fastpath):
     """Edge cases of n_eff (1, 2, P-2, P-1, P, all-zero channel) in the [B,res,res,res,20*S] layout."""
     w, mu, sg = grid_gmm(res, var)
@@ -284,6 +285,35 @@ def test_half2_mups_layout_against_oracle(res, P, S, var, fastpath):
     # channel layout is the same numbers transposed
     ch = mb.stats_3dmfv(pts, ne, mb.gmm_handle(w, mu, sg), S, layout="channel", fastpath=fastpath).cpu().numpy()
     assert np.array_equal(ch.transpose(0, 3, 1, 2).reshape(B, res, res, res, 20 * S), got.cpu().numpy())
+
+
+@pytest.mark.parametrize("variant,res,var", [(1, 8, 0.0156), (2, 8, 0.0156), (1, 4, 0.0625), (8, 16, 0.00390625),
+                                             (1, 16, 0.00390625)])
+def test_half2_kernel_variants(variant, res, var):
+    """The non-default statistics kernels kept for A/B measurements (mups_set_option "stats_variant": 1 = round-1
+    loop and staging, 2 = all-scalar loop, 8 = 16^3 without the cluster) compute the same features."""
+    w, mu, sg = grid_gmm(res, var)
+    rng = np.random.RandomState(variant * 100 + res)
+    P, S, B = 200, 2, 10
+    ne = rng.randint(1, P + 1, (B, S)).astype(np.int32)
+    ne[0] = [P, 1]
+    pts = np.zeros((B, S * P, 3), np.float32)
+    for b in range(B):
+        for s in range(S):
+            x = rng.normal(size=(ne[b, s], 3)) * 0.4
+            x /= np.maximum(1.0, np.linalg.norm(x, axis=1, keepdims=True))
+            x[0] = 0
+            pts[b, s * P: s * P + ne[b, s]] = x
+    gmm = mb.gmm_handle(w, mu, sg)
+    base = mb.stats_3dmfv(pts, ne, gmm, S).cpu().numpy()
+    try:
+        _lib.set_option("stats_variant", variant)
+        got = mb.stats_3dmfv(pts, ne, gmm, S).cpu().numpy()
+    finally:
+        _lib.set_option("stats_variant", 0)
+    ref = c_oracle.mups(pts, ne, w, mu, sg, S)
+    assert_features_close(got, ref, "variant %d res %d" % (variant, res), truth=lambda: f64_mups(pts, ne, w, mu, sg, S))
+    assert_features_close(base, ref, "default res %d" % res, truth=lambda: f64_mups(pts, ne, w, mu, sg, S))
 
 
 def test_half2_general_gmm_and_padding_rows():
