@@ -71,3 +71,45 @@ def get_data_loader(dataset_name='trainingset_temp.txt', batchSize=128, indir='.
     dataloader = PatchBatchLoader(dataset, sampler, batchSize)
     print(dataset_type + ' set: %d patches (in %d batches))' % (len(sampler), len(dataloader)))
     return (dataloader, dataset)
+
+
+# --------------------------------------------------------------------------------------------------
+# training-time rotation augmentation (train_n_est_w_experts.py:262-274), between half 1 and half 2
+# --------------------------------------------------------------------------------------------------
+
+def euler2mat(z=0.0, y=0.0, x=0.0):
+    """Rotation matrix Rx(x) . Ry(y) . Rz(z) with the reference's conventions (utils/eulerangles.py:
+    the factors for z, y, x are collected in that order, zero angles skipped, and multiplied in reverse)."""
+    import numpy as np
+    cz, sz, cy, sy, cx, sx = math.cos(z), math.sin(z), math.cos(y), math.sin(y), math.cos(x), math.sin(x)
+    rz = np.array([[cz, -sz, 0.0], [sz, cz, 0.0], [0.0, 0.0, 1.0]])
+    ry = np.array([[cy, 0.0, sy], [0.0, 1.0, 0.0], [-sy, 0.0, cy]])
+    rx = np.array([[1.0, 0.0, 0.0], [0.0, cx, -sx], [0.0, sx, cx]])
+    ms = [f for f, angle in ((rz, z), (ry, y), (rx, x)) if angle]
+    if not ms:
+        return np.eye(3)
+    m = ms[-1]                      # reduce(np.dot, Ms[::-1]): ((Rx . Ry) . Rz), same association -> same bits
+    for f in ms[-2::-1]:
+        m = np.dot(m, f)
+    return m
+
+
+def rotation_augmentation(points, normals, rng=None, angles=None):
+    """One random rotation per batch applied to the patches and the target normals, as the training loop
+    does when ``--insert_rotation_augmentation`` is set: ``angles = 2 pi randn(3)``,
+    ``R = euler2mat(z, y, x).T``, ``points[k] @ R`` and ``normals[k] @ R`` evaluated in float64 and
+    stored as float32.  ``points`` [B, S*P, 3] / ``normals`` [B, 3] may live on the GPU (the patches
+    of a batch stay on the device between the ball query and the statistics kernel).
+    Returns (rotated points, rotated normals, R)."""
+    import numpy as np
+    import torch
+    if angles is None:
+        rng = np.random if rng is None else rng
+        angles = 2 * np.pi * rng.randn(3)
+    R = np.transpose(euler2mat(z=angles[0], y=angles[1], x=angles[2]))
+    points = torch.as_tensor(points)
+    normals = torch.as_tensor(normals)
+    Rt = torch.as_tensor(R, dtype=torch.float64, device=points.device)
+    rp = torch.matmul(points.to(torch.float64), Rt).to(torch.float32)
+    rn = torch.matmul(normals.to(torch.float64), Rt.to(normals.device)).to(torch.float32)
+    return rp, rn, R

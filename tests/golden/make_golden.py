@@ -209,7 +209,34 @@ def make_half2_reference_numpy():
     np.savez_compressed(os.path.join(HERE, "half2_reference_numpy.npz"), **out)
 
 
+def make_rotation_reference():
+    """utils/eulerangles.py::euler2mat and the augmentation of train_n_est_w_experts.py:262-272 run on the
+    unmodified reference module (a py2 builtin, ``reduce``, is supplied from functools)."""
+    import functools
+    if REF_UTILS not in sys.path:
+        sys.path.insert(0, REF_UTILS)
+    import eulerangles as ref
+    ref.reduce = functools.reduce
+    rng = np.random.RandomState(0)
+    angles = [2 * np.pi * rng.randn(3) for _ in range(5)] + [np.array([0.2, 0.0, 0.3]), np.array([0.0, 0.0, 0.3]),
+                                                             np.zeros(3)]
+    mats = [ref.euler2mat(z=a[0], y=a[1], x=a[2]) for a in angles]
+    pts = rng.randn(4, 64, 3).astype(np.float32)
+    nrm = rng.randn(4, 3).astype(np.float32)
+    a = 2 * np.pi * rng.randn(3)
+    R = np.transpose(ref.euler2mat(z=a[0], y=a[1], x=a[2]))
+    rot = np.zeros(pts.shape, dtype=np.float32)
+    rotn = np.zeros(nrm.shape, dtype=np.float32)
+    for k in range(pts.shape[0]):                      # the loop of train_n_est_w_experts.py:267-271
+        rot[k, ...] = np.dot(pts[k, ...].reshape((-1, 3)), R)
+        rotn[k, ...] = np.dot(nrm[k, ...], R)
+    np.savez(os.path.join(HERE, "rotation_reference.npz"), angles=np.array(angles), mats=np.array(mats), aug_angles=a,
+             points=pts, normals=nrm, rotated_points=rot, rotated_normals=rotn)
+    print("rotation reference: %d matrices, batch %s" % (len(mats), pts.shape))
+
+
 if __name__ == "__main__":
     make_half1()
     make_half2_reference_numpy()
+    make_rotation_reference()
     make_half2()

@@ -169,6 +169,22 @@ def test_dataset_rejects_options_off_the_hot_path(tmp_path):
         mb.provider.get_data_loader(outputs=["bogus"], indir=str(tmp_path), dataset_name="list.txt")
 
 
+def test_rotation_augmentation_matches_reference_run(golden_dir):
+    """euler2mat and the per-batch rotation of train_n_est_w_experts.py:262-272, against outputs of the
+    reference's own utils/eulerangles.py (tests/golden/make_golden.py): bit-identical."""
+    ref = np.load(os.path.join(golden_dir, "rotation_reference.npz"))
+    for a, m in zip(ref["angles"], ref["mats"]):
+        assert np.array_equal(mb.provider.euler2mat(z=a[0], y=a[1], x=a[2]), m)
+    rp, rn, R = mb.provider.rotation_augmentation(ref["points"], ref["normals"], angles=ref["aug_angles"])
+    assert rp.dtype == torch.float32 and np.array_equal(rp.numpy(), ref["rotated_points"])
+    assert np.array_equal(rn.numpy(), ref["rotated_normals"])
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+    # random angles: 2 pi randn(3) from the supplied generator
+    _, _, R2 = mb.provider.rotation_augmentation(ref["points"], ref["normals"], rng=np.random.RandomState(5))
+    a = 2 * np.pi * np.random.RandomState(5).randn(3)
+    assert np.array_equal(R2, mb.provider.euler2mat(z=a[0], y=a[1], x=a[2]).T)
+
+
 def test_evaluation_metrics():
     """RMS angle / PGP5 / PGP10 as defined in the reference's utils/evaluate.py:133-154."""
     ev = mb.evaluate
