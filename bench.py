@@ -425,6 +425,8 @@ def run_own(args):
     # chunk: query points per pipeline stage.  Small enough that the first device->host copy starts ~1.5 ms after the
     # call (each cloud's call fills and drains the pipeline), large enough (336 MB per copy) for full PCIe rate.
     chunk = int(os.environ.get("MUPS_BENCH_CHUNK", "2048"))
+    if world > 1:
+        mb.dist.bind_to_gpu_numa_node(local_rank)     # pinned staging buffers on the GPU's NUMA node (no-op where sysfs has none)
     pipe = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=chunk if "e2e" not in skip else 64)
     hosts = [torch.from_numpy(c).pin_memory() for c in clouds_host]
     q_host = torch.arange(lo, hi, dtype=torch.int64).pin_memory()

@@ -66,3 +66,64 @@ def gather_slabs(slab, group=None):
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded.contiguous(), group=group)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# host placement: keep a rank's pinned staging buffers on the NUMA node its GPU hangs off
+# --------------------------------------------------------------------------------------------------
+
+def gpu_numa_info(device_index):
+    """PCI address and NUMA node of a CUDA device from sysfs (node -1: the platform does not say)."""
+    import os
+    info = {"device": int(device_index), "pci": None, "numa_node": -1, "cpus": None}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        info["pci"] = bdf
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            info["numa_node"] = int(f.read().strip())
+        if info["numa_node"] >= 0:
+            with open("/sys/devices/system/node/node%d/cpulist" % info["numa_node"]) as f:
+                info["cpus"] = f.read().strip()
+    except Exception:
+        pass
+    info["online_nodes"] = None
+    try:
+        with open("/sys/devices/system/node/online") as f:
+            info["online_nodes"] = f.read().strip()
+    except Exception:
+        pass
+    return info
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.update(range(int(lo), int(hi) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict this process to the CPUs of the GPU's NUMA node (first-touch then places the pinned
+    staging buffers there, so device->host copies do not cross the socket interconnect).  Returns True
+    when a binding was applied; silently does nothing where sysfs gives no node."""
+    import os
+    info = gpu_numa_info(device_index)
+    if info["numa_node"] < 0 or not info["cpus"]:
+        return False
+    try:
+        allowed = os.sched_getaffinity(0)
+        want = _parse_cpulist(info["cpus"]) & allowed
+        if not want:
+            return False
+        os.sched_setaffinity(0, want)
+        return True
+    except Exception:
+        return False

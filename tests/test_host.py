@@ -132,6 +132,16 @@ def _gloo_worker(rank, world, port, n_queries, ret):
         dist.destroy_process_group()
 
 
+def test_numa_binding_helpers_degrade_gracefully():
+    assert mb.dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    info = mb.dist.gpu_numa_info(0)                       # no GPU here: no PCI address, node -1
+    assert info["numa_node"] == -1 or info["cpus"]
+    before = os.sched_getaffinity(0)
+    applied = mb.dist.bind_to_gpu_numa_node(0)
+    assert applied or os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
+
+
 def test_gloo_world_size_2_slab_gather():
     world = 2
     mgr = mp.Manager()
