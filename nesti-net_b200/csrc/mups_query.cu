@@ -24,6 +24,8 @@ constexpr int kBins = 1 << kBinBits;
 constexpr int kBoundaryCap = 128;   // max entries of the threshold radix group resolved by rank counting
 constexpr int kHitCap = 4096;       // neighbours (any radius) kept in the shared-memory hit list
 constexpr int kRangeCap = 64;       // candidate cells per scan batch
+constexpr uint32_t kDenseCandidates = 3 * kHitCap;   // first-batch candidates above which the first scan also builds
+                                                     // the level-1 key histograms (dense balls re-scan per pass)
 
 struct QueryArgs {
     const float4* sorted;
@@ -58,6 +60,7 @@ struct QueryCtx {
 struct ScanTables {
     uint32_t start[kRangeCap];
     uint32_t prefix[kRangeCap + 1];
+    uint32_t first_total;           // candidates of the first batch of the last scan (all 27 cells when R = 1)
 };
 
 // cKDTree leaf predicate: s = 0; s += d*d for x, y, z in float64 without FMA contraction; s <= r*r
@@ -110,7 +113,10 @@ __device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx&
             st.start[2 * lane + 1] = beg[1];
             st.prefix[2 * lane] = exc;
             st.prefix[2 * lane + 1] = exc + cnt[0];
-            if (lane == 31) st.prefix[kRangeCap] = inc;
+            if (lane == 31) {
+                st.prefix[kRangeCap] = inc;
+                if (cbase == 0) st.first_total = inc;
+            }
         }
         __syncthreads();
         const uint32_t total = st.prefix[kRangeCap];
@@ -285,11 +291,20 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
         uint32_t cnt[MUPS_MAX_SCALES];
 #pragma unroll
         for (int s = 0; s < NS; ++s) cnt[s] = 0u;
-        for_each_hit<NS>(a, c, st, [&](uint32_t pos, uint32_t, uint32_t in) {
+        for_each_hit<NS>(a, c, st, [&](uint32_t pos, uint32_t idx, uint32_t in) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) cnt[s] += (in >> s) & 1u;
             const uint32_t slot = atomicAdd(&s_nhits, 1u);
             if (slot < (uint32_t)kHitCap) { hit_pos[slot] = pos; hit_mask[slot] = (unsigned char)in; }
+            if (st.first_total > kDenseCandidates) {
+                // dense neighbourhood: the hit list will overflow and every later pass re-scans the cells, so
+                // the level-1 key histograms of all radii are built here and one full scan is saved
+                uint32_t key[MUPS_MAX_SCALES];
+                selection_keys<NS>(salt, idx, in, key);
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if (in & (1u << s)) atomicAdd(hist + s * kBins + (key[s] >> (32 - kBinBits)), 1u);
+            }
         });
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -334,9 +349,10 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
         }
     };
 
+    const bool fused_hist = st.first_total > kDenseCandidates;   // uniform: written once per scan, read after barriers
     if (over) {
         // ---- first-level key histogram of the over-full radii ------------------------------------------
-        visit(over, [&](uint32_t, uint32_t idx, uint32_t in) {
+        if (!fused_hist) visit(over, [&](uint32_t, uint32_t idx, uint32_t in) {
             in &= over;
             uint32_t key[MUPS_MAX_SCALES];
             selection_keys<NS>(salt, idx, in, key);

@@ -47,7 +47,7 @@ def run(name, pts, radius, P, res, n_queries, n_check, kdtree=None):
     gmm = mb.gmm_handle(w, mu, sg)
     S = len(radius)
     xyz = torch.from_numpy(pts).cuda()
-    t_build, index = timed(lambda: mb.PointIndex(xyz, cell_frac=max(radius)))
+    t_build, index = timed(lambda: mb.PointIndex(xyz, cell_frac=max(radius), cell_scale=float(os.environ['CELL_SCALE']) if os.environ.get('CELL_SCALE') else None))
     radii = index.absolute_radii(radius)
     q = (np.arange(n_queries, dtype=np.int64) * (n // n_queries) + 17) % n
     qd = torch.from_numpy(q).cuda()

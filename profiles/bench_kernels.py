@@ -41,8 +41,8 @@ def main():
     g = mb.get_3d_grid_gmm([res] * 3, var)
     gmm = mb.gmm_handle(g.weights_, g.means_, np.sqrt(g.covariances_))
     xyz = torch.from_numpy(pts).cuda()
-    t_build = timed(lambda: mb.PointIndex(xyz, cell_frac=max(radius)))
-    index = mb.PointIndex(xyz, cell_frac=max(radius))
+    t_build = timed(lambda: mb.PointIndex(xyz, cell_frac=max(radius), cell_scale=float(os.environ['CELL_SCALE']) if os.environ.get('CELL_SCALE') else None))
+    index = mb.PointIndex(xyz, cell_frac=max(radius), cell_scale=float(os.environ['CELL_SCALE']) if os.environ.get('CELL_SCALE') else None)
     radii = index.absolute_radii(radius)
     q = torch.from_numpy(np.random.RandomState(0).choice(n, nq, replace=nq > n)).cuda()
     out = {}

@@ -142,6 +142,24 @@ def test_half1_against_oracle(n, P, radius, kind, seed):
     assert (total > P).any() and (total <= P).any()      # both branches exercised
 
 
+def test_half1_grid_cell_scale():
+    """Dense clouds get finer grid cells (mb.mups.grid_cell_scale): same neighbours, same patches."""
+    assert mb.mups.grid_cell_scale(100000) == 1.0 and mb.mups.grid_cell_scale(450000) == 0.5
+    assert mb.mups.grid_cell_scale(10000000) == 0.34
+    radius, P = [0.01, 0.03, 0.07], 256
+    for n, scale in ((450000, None), (60000, 0.34), (60000, 0.5)):
+        pts = orc.synthetic_cloud(n, cloud_id=11, kind="scan" if n > 100000 else "pcpnet", noise=0.001)
+        q = np.random.RandomState(5).choice(n, 24, replace=False)
+        index = mb.PointIndex(pts, cell_frac=max(radius), cell_scale=scale)
+        patches, n_eff, total, nbr = index.ball_query(torch.from_numpy(q).cuda(), index.absolute_radii(radius), P,
+                                                      seed=SEED, return_indices=True)
+        o_patches, o_neff, o_total, o_nbr = orc.gather_patches(pts, q, radius, P, seed=SEED, return_indices=True)
+        assert np.array_equal(total.cpu().numpy(), o_total), (n, scale)
+        assert np.array_equal(nbr.cpu().numpy(), o_nbr), (n, scale)
+        assert np.array_equal(patches.cpu().numpy().view(np.uint32), o_patches.view(np.uint32)), (n, scale)
+        assert np.array_equal(n_eff.cpu().numpy(), o_neff)
+
+
 def test_half1_edge_cases():
     rng = np.random.RandomState(2)
     # single point, two identical points, tiny cloud
