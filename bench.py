@@ -457,6 +457,39 @@ def run_own(args):
            "chunk_queries": pipe.chunk,
            "api": "MuPSPipeline.features_to_host (pinned host cloud in, MuPS rows streamed to pinned host memory)"}
 
+    # the same call with the consumer on the device (what the reference's inference loop does with MuPS: it feeds the
+    # 3D-CNN and never visits the host): host cloud in, features reduced to one checksum on the GPU, 8 bytes read back
+    if "e2e" not in skip:
+        acc = torch.zeros((), dtype=torch.float64, device=dev)
+        pipe_dev = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=16384)     # no PCIe stage to feed: larger chunks
+
+        def on_device(lo_, hi_, rows_):
+            acc.add_(rows_.sum())
+
+        def dev_step(i):
+            n = 0
+            for c in range(n_gpus):
+                n += pipe_dev.features_to_consumer(hosts[(i * n_gpus + c) % len(hosts)], q_host, on_device)
+            return n
+
+        dev_step(0)
+        barrier()
+        pipe_dev.h2d_bytes = 0
+        w0 = time.perf_counter()
+        n_dev = 0
+        for i in range(e2e_steps):
+            n_dev += dev_step(1 + i)
+        checksum = float(acc.item())                       # the device->host read of the step's result
+        dc_s = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dc_s, op=dist.ReduceOp.MAX)
+        barrier()
+        e2e["device_consumer"] = {"value": n_dev * n_gpus / float(dc_s.item()), "unit": UNIT,
+                                  "h2d_bytes_per_step": pipe_dev.h2d_bytes // e2e_steps, "d2h_bytes_per_step": 8,
+                                  "chunk_queries": pipe_dev.chunk,
+                                  "checksum_finite": bool(np.isfinite(checksum)),
+                                  "api": "MuPSPipeline.features_to_consumer (host cloud in, MuPS reduced on the GPU)"}
+
     cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                     "sample": "measured at N=1 only (see the N=1 line / --impl reference)"}
     if rank == 0 and n_gpus == 1:

@@ -500,6 +500,18 @@ def test_sharded_slabs_and_host_pipeline():
     assert pipe.d2h_bytes == got.nbytes and pipe.h2d_bytes == pts.nbytes
     dev = pipe.features_on_device(pts, q[:100])
     assert torch.equal(dev, full[:100])
+    # consumer on the device (the reference's flow: MuPS feeds the CNN and never visits the host)
+    kept = torch.zeros((n, 20 * 2 * 512), dtype=torch.float32, device="cuda")
+    sub = np.arange(5, n, 3, dtype=np.int64)
+    chunks = []
+
+    def on_device(lo, hi, rows):
+        assert rows.is_cuda and tuple(rows.shape) == (hi - lo, 20 * 2 * 512)
+        kept[lo:hi].copy_(rows)
+        chunks.append((lo, hi))
+    assert pipe.features_to_consumer(torch.from_numpy(pts), sub, on_device) == len(sub)
+    assert chunks[0] == (0, 1024) and chunks[-1][1] == len(sub)
+    assert torch.equal(kept[:len(sub)], full.reshape(n, -1)[torch.from_numpy(sub).cuda()])
 
 
 def test_inference_driver(tmp_path):
