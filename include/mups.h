@@ -70,7 +70,10 @@ int64_t mups_launch_count(void);
 /* Process-wide tuning knobs.  "boundary_cap" (1..512, default 512): largest radix threshold group
  * the subsample resolves without another refinement level (tests lower it to exercise the
  * refinement path, which otherwise needs > ~500k neighbours in one ball).
- * "stats_variant" (0 = automatic): force a statistics-kernel variant (benchmarking only). */
+ * "fuse_candidates" (default 12288): candidate points in a ball's first cell batch above which the
+ * first scan also builds the subsample's key histograms (dense balls; results never depend on it).
+ * "stats_variant" (0 = automatic; 1 round-1 loop and staging, 2 all-scalar loop, 8 no cluster at 16^3):
+ * force a statistics-kernel variant (benchmarking only). */
 int mups_set_option(const char* name, int64_t value);
 
 /* ---- spatial index (K1 bbox + K2 grid build) --------------------------------------------- */

@@ -12,6 +12,7 @@ namespace mups {
 static thread_local char t_error[512] = "";
 std::atomic<int64_t> g_launch_count{0};
 std::atomic<int> g_boundary_cap{512};
+std::atomic<int> g_fuse_candidates{3 * 4096};
 std::atomic<int> g_stats_variant{0};
 
 void set_error(const char* fmt, ...) {
@@ -80,6 +81,11 @@ int mups_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "boundary_cap")) {
         MUPS_REQUIRE(value >= 1 && value <= 512, "mups_set_option: boundary_cap=%lld out of range [1, 512]", (long long)value);
         g_boundary_cap.store((int)value);
+        return MUPS_OK;
+    }
+    if (!strcmp(name, "fuse_candidates")) {
+        MUPS_REQUIRE(value >= 0 && value <= 0x7FFFFFFF, "mups_set_option: fuse_candidates=%lld out of range", (long long)value);
+        g_fuse_candidates.store((int)value);
         return MUPS_OK;
     }
     if (!strcmp(name, "stats_variant")) {

@@ -21,6 +21,7 @@ constexpr int kNumSMs = 148;  // B200
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launch_count;
 extern std::atomic<int> g_boundary_cap;
+extern std::atomic<int> g_fuse_candidates;
 extern std::atomic<int> g_stats_variant;
 
 #define MUPS_CUDA_TRY(expr)                                                                   \

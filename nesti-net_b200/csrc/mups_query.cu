@@ -24,8 +24,8 @@ constexpr int kBins = 1 << kBinBits;
 constexpr int kBoundaryCap = 128;   // max entries of the threshold radix group resolved by rank counting
 constexpr int kHitCap = 4096;       // neighbours (any radius) kept in the shared-memory hit list
 constexpr int kRangeCap = 64;       // candidate cells per scan batch
-constexpr uint32_t kDenseCandidates = 3 * kHitCap;   // first-batch candidates above which the first scan also builds
-                                                     // the level-1 key histograms (dense balls re-scan per pass)
+// first-batch candidates above which the first scan also builds the level-1 key histograms (default 3 * kHitCap:
+// balls whose hit list will overflow and that re-scan the cells in every pass); mups_set_option("fuse_candidates")
 
 struct QueryArgs {
     const float4* sorted;
@@ -36,6 +36,7 @@ struct QueryArgs {
     int64_t n;
     int S, P, Ppad;
     int cap;                        // threshold groups up to this size are resolved by rank counting
+    uint32_t fuse;                  // see g_fuse_candidates
     double r2[MUPS_MAX_SCALES];     // r*r in float64 (cKDTree's upper bound for p=2)
     float r2_lo[MUPS_MAX_SCALES];   // fp32 guard band around r2: below -> inside, above hi -> outside
     float r2_hi[MUPS_MAX_SCALES];
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
             for (int s = 0; s < NS; ++s) cnt[s] += (in >> s) & 1u;
             const uint32_t slot = atomicAdd(&s_nhits, 1u);
             if (slot < (uint32_t)kHitCap) { hit_pos[slot] = pos; hit_mask[slot] = (unsigned char)in; }
-            if (st.first_total > kDenseCandidates) {
+            if (st.first_total > a.fuse) {
                 // dense neighbourhood: the hit list will overflow and every later pass re-scans the cells, so
                 // the level-1 key histograms of all radii are built here and one full scan is saved
                 uint32_t key[MUPS_MAX_SCALES];
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
         }
     };
 
-    const bool fused_hist = st.first_total > kDenseCandidates;   // uniform: written once per scan, read after barriers
+    const bool fused_hist = st.first_total > a.fuse;   // uniform: written once per scan, read after barriers
     if (over) {
         // ---- first-level key histogram of the over-full radii ------------------------------------------
         if (!fused_hist) visit(over, [&](uint32_t, uint32_t idx, uint32_t in) {
@@ -543,6 +544,7 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
     while (ppad < P) ppad <<= 1;
     a.Ppad = ppad;
     a.cap = g_boundary_cap.load();
+    a.fuse = (uint32_t)g_fuse_candidates.load();
     double rmax = 0.0;
     float hi_max = 0.f;
     for (int s = 0; s < MUPS_MAX_SCALES; ++s) {

@@ -46,6 +46,10 @@ def main():
     radii = index.absolute_radii(radius)
     q = torch.from_numpy(np.random.RandomState(0).choice(n, nq, replace=nq > n)).cuda()
     out = {}
+    for fuse in [int(v) for v in os.environ.get("FUSE", "").split(",") if v]:
+        _lib.set_option("fuse_candidates", fuse)
+        print(json.dumps({"fuse_candidates": fuse, "ball_query_ms": timed(lambda: index.ball_query(q, radii, P), iters=10, warm=3)}))
+    _lib.set_option("fuse_candidates", 12288)
     t_query = timed(lambda: index.ball_query(q, radii, P))
     patches, n_eff, total = index.ball_query(q, radii, P)
     ne = n_eff.cpu().numpy()

@@ -231,8 +231,19 @@ def test_half1_cell_size_independent_and_refinement_levels():
             _, _, out = run_half1(pts, q[:24], big, 128)
             for a, b in zip(out, ref_big):
                 assert np.array_equal(a, b), "re-scan path, boundary_cap=%d" % cap
+        # ... and with the key histograms built in the first scan for every ball / for none
+        _lib.set_option("boundary_cap", 512)
+        for fuse in (0, 2 ** 31 - 1):
+            _lib.set_option("fuse_candidates", fuse)
+            _, _, out = run_half1(pts, q, radius, 128, cell_frac=0.1)
+            for a, b in zip(out, ref):
+                assert np.array_equal(a, b), "fuse_candidates=%d" % fuse
+            _, _, out = run_half1(pts, q[:24], big, 128)
+            for a, b in zip(out, ref_big):
+                assert np.array_equal(a, b), "re-scan path, fuse_candidates=%d" % fuse
     finally:
         _lib.set_option("boundary_cap", 512)
+        _lib.set_option("fuse_candidates", 12288)
     perm = np.random.RandomState(4).permutation(len(q))
     _, _, out = run_half1(pts, q[perm], radius, 128, cell_frac=0.1)
     for a, b in zip(out, ref):

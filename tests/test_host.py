@@ -51,6 +51,10 @@ def test_argument_validation_without_compute():
     assert L.mups_set_option(b"no_such_option", 1) == _lib.MUPS_ERR_INVALID
     assert L.mups_set_option(b"boundary_cap", 0) == _lib.MUPS_ERR_INVALID
     assert L.mups_set_option(b"boundary_cap", 512) == _lib.MUPS_OK
+    assert L.mups_set_option(b"fuse_candidates", -1) == _lib.MUPS_ERR_INVALID
+    assert L.mups_set_option(b"fuse_candidates", 12288) == _lib.MUPS_OK
+    assert L.mups_set_option(b"stats_variant", 65) == _lib.MUPS_ERR_INVALID
+    assert L.mups_set_option(b"stats_variant", 0) == _lib.MUPS_OK
     with pytest.raises(ValueError):
         _lib.check(L.mups_set_option(b"boundary_cap", 100000))
     if not torch.cuda.is_available():
