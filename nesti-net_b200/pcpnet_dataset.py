@@ -147,6 +147,7 @@ class PointcloudPatchDataset(torch.utils.data.Dataset):
         self.point_tuple = point_tuple
         self.point_count_std = point_count_std
         self.seed = int(np.random.randint(0, 2 ** 32 - 1)) if seed is None else int(seed)
+        self.epoch = 0
 
         if center not in ('point', 'mean', 'none'):
             raise ValueError('Unknown patch centering option: %s' % (center))
@@ -186,6 +187,20 @@ class PointcloudPatchDataset(torch.utils.data.Dataset):
             # bbdiag from the device bbox, evaluated with the reference's own numpy expression
             self.patch_radius_absolute.append(shape.index.absolute_radii(self.patch_radius))
         self._offsets = np.concatenate([[0], np.cumsum(self.shape_patch_count)]).astype(np.int64)
+
+    # ---- subsample seed per epoch -----------------------------------------------------------------
+    def begin_epoch(self):
+        """Called by the batch loader at the start of every pass.  The reference draws its subsamples from one
+        stateful stream, so a patch gets a different 512-point subset in every epoch unless ``identical_epochs``
+        reseeds it per item (pcpnet_dataset.py:306-308); here the selection is a pure function of (seed, centre,
+        scale), and the epoch enters through the seed instead."""
+        if not self.identical_epochs:
+            self.epoch += 1
+
+    def selection_seed(self):
+        """64-bit seed of the shared seeded selection for the current epoch (epoch 0 and every epoch of an
+        ``identical_epochs`` dataset: the constructor's seed)."""
+        return (self.seed + self.epoch * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
 
     # ---- reference-compatible per-item access (:286-419) ---------------------------------------
     def __getitem__(self, index):
@@ -240,7 +255,7 @@ class PointcloudPatchDataset(torch.utils.data.Dataset):
             local = indices[start:end] - self._offsets[shape_ind]
             c = local if shape.pidx is None else shape.pidx[local]
             centers[start:end] = c
-            p, ne, _ = shape.index.ball_query(c, self.patch_radius_absolute[shape_ind], P, seed=self.seed)
+            p, ne, _ = shape.index.ball_query(c, self.patch_radius_absolute[shape_ind], P, seed=self.selection_seed())
             points[start:end] = p
             n_eff[start:end] = ne
             start = end

@@ -17,12 +17,16 @@ class PatchBatchLoader(object):
         self.dataset = dataset
         self.sampler = sampler
         self.batch_size = int(batch_size)
+        self._started = False
 
     def __len__(self):
         return int(math.ceil(len(self.sampler) / float(self.batch_size)))
 
     def __iter__(self):
         batch = []
+        if self._started and hasattr(self.dataset, "begin_epoch"):
+            self.dataset.begin_epoch()          # a fresh subsample per epoch unless identical_epochs
+        self._started = True
         for idx in self.sampler:
             batch.append(int(idx))
             if len(batch) == self.batch_size:

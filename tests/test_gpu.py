@@ -420,6 +420,20 @@ def test_dataset_drop_in(tmp_path, half1):
     assert tuple(points.shape) == (64, S * P, 3) and tuple(trans.shape) == (64, 3, 3) and tuple(ne.shape) == (64, S)
     ref_p, ref_ne, _ = orc.gather_patches(pts, np.arange(64), radius, P, seed=SEED)
     assert np.array_equal(points.cpu().numpy(), ref_p) and np.array_equal(ne.cpu().numpy(), ref_ne.astype(np.float64))
+    # epochs: a second pass over the loader draws fresh subsamples (the reference's stateful stream does), the
+    # oracle reproduces them from the epoch's seed; identical_epochs keeps the first pass's subsamples
+    second = next(iter(loader))
+    assert dataset.epoch == 1 and dataset.selection_seed() != SEED
+    ref_p2, ref_ne2, _ = orc.gather_patches(pts, np.arange(64), radius, P, seed=dataset.selection_seed())
+    assert np.array_equal(second[0].cpu().numpy(), ref_p2) and np.array_equal(second[-1].cpu().numpy(), ref_ne2.astype(np.float64))
+    assert (ref_ne > P - 1).any() and not np.array_equal(ref_p2, ref_p)            # some patch was subsampled differently
+    assert np.array_equal(second[-1].cpu().numpy(), ne.cpu().numpy())               # counts do not depend on the draw
+    ds_same = mb.pcpnet_dataset.PointcloudPatchDataset(
+        root=str(tmp_path), shape_list_filename="list.txt", patch_radius=radius, points_per_patch=P,
+        patch_features=[], seed=SEED, identical_epochs=True, use_pca=False, center="point",
+        point_tuple=1, cache_capacity=100, point_count_std=0, sparse_patches=False)
+    ds_same.begin_epoch()
+    assert ds_same.epoch == 0 and ds_same.selection_seed() == SEED
 
 
 def test_full_size_properties():
