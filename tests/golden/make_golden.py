@@ -20,7 +20,9 @@ half2_reference_numpy.npz -- outputs of the reference's own numpy code run
     graph) and ``utils/utils.py::get_3DmFV`` (:260-330).  The latter differs
     from the TF path in ONE stage (it takes Q = p, no posterior normalisation,
     and has no mask), so it pins every other stage of the half-2 restatement
-    (``get_3dmfv_n_est(..., _posterior="pdf")``) against the reference itself.
+    (``get_3dmfv_n_est(..., _posterior="pdf")``) against the reference itself; and
+    ``utils/utils.py::fisher_vector_per_point`` (:214-245), whose per-point terms use the posterior
+    (sklearn ``predict_proba``) and pin that stage too.  Only the n_eff mask exists in the TF code alone.
 half2_oracle.npz -- inputs/outputs of the recorded fp32 transliteration of
     utils/tf_util.py:655-753 / :578-652 (TensorFlow 1.12 is not installable:
     PARITY UNPINNED), written only after the independent float64 restatement
@@ -206,6 +208,39 @@ def make_half2_reference_numpy():
               float(np.abs(mine - fv).max()))
         out.update({name + "_points": pts, name + "_w": w, name + "_mu": mu, name + "_sigma": sigma,
                     name + "_fv": np.asarray(fv, np.float64), name + "_fv_raw": np.asarray(fv_raw, np.float64)})
+    # The posterior stage: the reference's fisher_vector_per_point (utils/utils.py:214-245) evaluates the per-point
+    # derivative terms with Q = gmm.predict_proba(xx) (sklearn, float64) -- the posterior w p / sum_g w p of
+    # tf_util.py:700-701 -- including the 1/sqrt(w), 1/sqrt(2w) factors.  Reduced over the points with the statements of
+    # the reference's own get_3DmFV tail (:302-326: max/min/sum, /n_points, signed sqrt, l2_normalize, channel order)
+    # this is get_3dmfv_n_est with nothing masked.
+    for name, res, var, B, P in (("post_g3", 3, 0.11, 5, 16), ("post_g8", 8, 0.0156, 3, 64)):
+        gmm = ref_utils.get_3d_grid_gmm(subdivisions=[res] * 3, variance=var)
+        w, mu, sigma = (np.asarray(gmm.weights_, np.float32), np.asarray(gmm.means_, np.float32),
+                        np.sqrt(gmm.covariances_).astype(np.float32))
+        x = rng.normal(size=(B, P, 3)) * 0.4
+        x /= np.maximum(1.0, np.linalg.norm(x, axis=2, keepdims=True))
+        x[:, 0] = 0.0
+        pts = x.astype(np.float32)
+        fv = []
+        for b in range(B):
+            d_pi_all, d_mu_all, d_sig_all = ref_utils.fisher_vector_per_point(pts[b].astype(np.float64), gmm)
+            d_pi = np.concatenate([np.max(d_pi_all[..., None], axis=0), np.sum(d_pi_all[..., None], axis=0)], axis=1)
+            d_mu = np.concatenate([np.max(d_mu_all, axis=0), np.min(d_mu_all, axis=0), np.sum(d_mu_all, axis=0)], axis=1)
+            d_sigma = np.concatenate([np.max(d_sig_all, axis=0), np.min(d_sig_all, axis=0), np.sum(d_sig_all, axis=0)], axis=1)
+            d_pi, d_mu, d_sigma = d_pi / P, d_mu / P, d_sigma / P
+            alpha = 0.5
+            d_pi = np.sign(d_pi) * np.power(np.abs(d_pi), alpha)
+            d_mu = np.sign(d_mu) * np.power(np.abs(d_mu), alpha)
+            d_sigma = np.sign(d_sigma) * np.power(np.abs(d_sigma), alpha)
+            d_pi = ref_utils.l2_normalize(d_pi, dim=0)
+            d_mu = ref_utils.l2_normalize(d_mu, dim=0)
+            d_sigma = ref_utils.l2_normalize(d_sigma, dim=0)
+            fv.append(np.concatenate([d_pi, d_mu, d_sigma], axis=1).T)          # [20, G]
+        fv = np.asarray(fv)
+        mine = orc.get_3dmfv_n_est(pts, w, mu, sigma, flatten=False, n_original_points=np.full(B, P, np.int32))
+        print("half2 posterior case", name, fv.shape, "oracle vs reference (sklearn posterior) max abs err",
+              float(np.abs(mine - fv).max()))
+        out.update({name + "_points": pts, name + "_w": w, name + "_mu": mu, name + "_sigma": sigma, name + "_fv": fv})
     np.savez_compressed(os.path.join(HERE, "half2_reference_numpy.npz"), **out)
 
 

@@ -266,6 +266,23 @@ def test_half2_against_golden_fixture(half2, case, fastpath):
     assert_features_close(got, half2[case + "_fv_plain"], case + " plain")
 
 
+@pytest.mark.parametrize("fastpath", [True, False])
+@pytest.mark.parametrize("case", ["post_g3", "post_g8"])
+def test_half2_against_reference_run_fixture(golden_dir, case, fastpath):
+    """CUDA kernels against outputs of the REFERENCE's own numpy code run in the build container (posterior from
+    sklearn predict_proba through utils/utils.py::fisher_vector_per_point, reductions and normalisations of its
+    get_3DmFV; tests/golden/make_golden.py): the path with nothing masked."""
+    ref = np.load(os.path.join(golden_dir, "half2_reference_numpy.npz"))
+    pts, w, mu, sg = (ref["%s_%s" % (case, k)] for k in ("points", "w", "mu", "sigma"))
+    B, P, _ = pts.shape
+    gmm = mb.gmm_handle(w, mu, sg)
+    got = mb.stats_3dmfv(pts, np.full((B, 1), P, np.int32), gmm, 1, masked=True, layout="channel",
+                         fastpath=fastpath).cpu().numpy()[:, 0]
+    assert_features_close(got, ref[case + "_fv"], case + " vs reference run")
+    plain = mb.stats_3dmfv(pts, None, gmm, 1, masked=False, layout="channel", fastpath=fastpath).cpu().numpy()[:, 0]
+    assert_features_close(plain, ref[case + "_fv"], case + " get_3dmfv vs reference run")     # isotropic sigma: same pdf
+
+
 def test_half2_reference_signatures(half2):
     """tf_util.get_3dmfv_n_est / get_3dmfv drop-ins: names, argument meaning, flatten, errors."""
     pts, ne, w, mu, sg = (half2["g8_%s" % k] for k in ("points", "n_eff", "w", "mu", "sigma"))

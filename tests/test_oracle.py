@@ -152,6 +152,27 @@ def test_half2_fixture_regression_and_c_port(half2, case):
     assert np.all((np.abs(nrm - 1) < 1e-5) | (nrm == 0))
 
 
+@pytest.mark.parametrize("case", ["post_g3", "post_g8"])
+def test_half2_posterior_stage_pinned_by_reference(half2_ref, case):
+    """The reference's fisher_vector_per_point (utils/utils.py:214-245, run unmodified by make_golden.py) evaluates
+    the per-point terms with the posterior Q = gmm.predict_proba(x) = w p / sum_g w p (tf_util.py:700-701); reduced
+    with the reference's own get_3DmFV tail it is get_3dmfv_n_est with nothing masked: the full restatement -- and
+    its C port and float64 twin -- must reproduce it."""
+    pts, w, mu, sg = (half2_ref["%s_%s" % (case, k)] for k in ("points", "w", "mu", "sigma"))
+    B, P, _ = pts.shape
+    ref = half2_ref[case + "_fv"]
+    ne = np.full(B, P, np.int32)
+    got = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False, n_original_points=ne)
+    assert frac_outside(got, ref) == 0.0, np.abs(got - ref).max()
+    assert frac_outside(c_oracle.get_3dmfv(pts, w, mu, sg, ne, masked=True), ref) == 0.0
+    # the float64 twin is fed the float32-rounded GMM the graph gets, the reference run its float64 sklearn object
+    assert np.abs(orc.get_3dmfv_n_est_f64(pts, w, mu, sg, ne, masked=True) - ref).max() < 1e-6
+    # n_eff = P - 1 masks nothing either (tf_util.py:696 masks r > n_eff) but divides by P - 1: same features, the
+    # positive factor cancels in the channel norm
+    got2 = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False, n_original_points=ne - 1)
+    assert frac_outside(got2, ref) == 0.0
+
+
 def test_mask_off_by_one_and_padding_semantics():
     """tf_util.py:696 masks r > n_eff: slot n_eff (a zero pad) takes part, slot n_eff+1 does not;
     masked slots feed exact zeros into max/min."""
