@@ -758,7 +758,7 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
     if (log_res == 4 && variant != 8 && items * 8 <= 0x7FFFFFFFll) {
         // 16^3 lattice: one thread-block cluster of 8 CTAs per (query, scale), tables shared through DSMEM
         constexpr int kCl = 8;
-        auto kern = stats_separable_kernel<0, 4, kCl, 0>;
+        auto kern = variant == 1 ? stats_separable_kernel<0, 4, kCl, 0> : stats_separable_kernel<1, 4, kCl, 0>;
         const size_t smem_cl = (size_t)(kSepClusterTilePoints / 2) * 3 * 16 * (sizeof(float4) + sizeof(float2)) +
                                sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P + kCl * 20);
         MUPS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl));

@@ -42,23 +42,28 @@ class MuPSPipeline(object):
             query_idx = torch.arange(index.n, dtype=torch.int64, device=self.device)
         return _m.mups_features(index, self.gmm, query_idx, radii, self.P, seed=self.seed, out=out)
 
-    def features_to_consumer(self, pts_host, query_idx_host, consume):
-        """Host cloud in, MuPS consumed ON THE DEVICE chunk by chunk -- the flow of the reference's inference
-        loop, where MuPS is an intermediate of the graph that feeds the 3D-CNN and never visits the host
-        (models/experts_n_est.py:59-108).  `consume(lo, hi, rows)` gets a CUDA view [hi-lo, 20*S*G] on the current
-        stream (valid until the next chunk is enqueued on that stream).  Returns the number of query points."""
+    def _stage_in(self, pts_host, query_idx_host):
+        """Host cloud (and query list) to the device, index build, radii: the front end shared by both streaming calls."""
         dev = self.device
         pts_host = torch.as_tensor(pts_host, dtype=torch.float32)
         xyz = pts_host.to(dev, non_blocking=True)
         self.h2d_bytes += pts_host.numel() * 4
         index = _m.PointIndex(xyz, cell_frac=max(self.patch_radius), device=dev)
-        radii = index.absolute_radii(self.patch_radius)
+        radii = index.absolute_radii(self.patch_radius)          # the one small synchronising read (bbox)
         if query_idx_host is None:
             q = torch.arange(index.n, dtype=torch.int64, device=dev)
         else:
             qh = torch.as_tensor(query_idx_host, dtype=torch.int64)
             q = qh.to(dev, non_blocking=True)
             self.h2d_bytes += qh.numel() * 8
+        return index, radii, q
+
+    def features_to_consumer(self, pts_host, query_idx_host, consume):
+        """Host cloud in, MuPS consumed ON THE DEVICE chunk by chunk -- the flow of the reference's inference
+        loop, where MuPS is an intermediate of the graph that feeds the 3D-CNN and never visits the host
+        (models/experts_n_est.py:59-108).  `consume(lo, hi, rows)` gets a CUDA view [hi-lo, 20*S*G] on the current
+        stream (valid until the next chunk is enqueued on that stream).  Returns the number of query points."""
+        index, radii, q = self._stage_in(pts_host, query_idx_host)
         B = int(q.shape[0])
         for c, lo in enumerate(range(0, B, self.chunk)):
             hi = min(B, lo + self.chunk)
@@ -71,19 +76,8 @@ class MuPSPipeline(object):
         """Streams the MuPS rows of every query of one cloud to the host.  `consume(lo, hi, rows)`
         is called with a pinned numpy view [hi-lo, 20*S*G] per chunk (valid only during the call).
         Returns the number of query points processed."""
-        dev = self.device
-        compute = torch.cuda.current_stream(dev)
-        pts_host = torch.as_tensor(pts_host, dtype=torch.float32)
-        xyz = pts_host.to(dev, non_blocking=True)
-        self.h2d_bytes += pts_host.numel() * 4
-        index = _m.PointIndex(xyz, cell_frac=max(self.patch_radius), device=dev)
-        radii = index.absolute_radii(self.patch_radius)          # the one small synchronising read (bbox)
-        if query_idx_host is None:
-            q = torch.arange(index.n, dtype=torch.int64, device=dev)
-        else:
-            qh = torch.as_tensor(query_idx_host, dtype=torch.int64)
-            q = qh.to(dev, non_blocking=True)
-            self.h2d_bytes += qh.numel() * 8
+        compute = torch.cuda.current_stream(self.device)
+        index, radii, q = self._stage_in(pts_host, query_idx_host)
         B = int(q.shape[0])
         pending = [None, None]
 
