@@ -53,6 +53,9 @@ typedef enum mups_status {
 #define MUPS_LAYOUT_MUPS 0u        /* out[b][g][s*20+c]  == [B,res,res,res,20*S] (experts_n_est.py:71-76) */
 #define MUPS_LAYOUT_CHANNEL 2u     /* out[b][s][c][g]    == per scale [B,20*G] flatten=True / [B,20,G] */
 #define MUPS_FLAG_NO_FASTPATH 4u   /* force the general (non-separable) statistics kernel */
+#define MUPS_FLAG_WIDE_STORES 8u   /* lattice kernel, MUPS layout: transpose a (query, scale) result through shared memory
+                                      and write it as 80-byte runs (5 lanes per Gaussian) instead of 16-byte pieces at a
+                                      320-byte stride -- for `out_dev` in a PEER GPU's memory (NVLink write efficiency) */
 
 /* limits compiled into the kernels */
 #define MUPS_MAX_SCALES 8

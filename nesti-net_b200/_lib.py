@@ -20,6 +20,7 @@ FLAG_MASKED = 1
 LAYOUT_MUPS = 0
 LAYOUT_CHANNEL = 2
 FLAG_NO_FASTPATH = 4
+FLAG_WIDE_STORES = 8
 MAX_SCALES = 8
 MAX_POINTS_PER_PATCH = 2048
 

@@ -329,7 +329,7 @@ int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_e
     MUPS_REQUIRE(B == 0 || (patches_dev && out_dev), "mups_3dmfv: patches / out is NULL");
     MUPS_REQUIRE(!(flags & MUPS_FLAG_MASKED) || B == 0 || n_eff_dev, "mups_3dmfv: n_eff is required with MUPS_FLAG_MASKED "
                  "(the reference fails on n_original_points=None, tf_util.py:665)");
-    MUPS_REQUIRE((flags & ~(MUPS_FLAG_MASKED | MUPS_LAYOUT_CHANNEL | MUPS_FLAG_NO_FASTPATH)) == 0, "mups_3dmfv: unknown flags 0x%x", flags);
+    MUPS_REQUIRE((flags & ~(MUPS_FLAG_MASKED | MUPS_LAYOUT_CHANNEL | MUPS_FLAG_NO_FASTPATH | MUPS_FLAG_WIDE_STORES)) == 0, "mups_3dmfv: unknown flags 0x%x", flags);
     if (int rc = check_device(gmm->device, "mups_3dmfv")) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // stream-ordered scratch for the fast path's fallback worklist (1 counter + one id per (query, scale))

@@ -676,7 +676,33 @@ __global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_ke
         __syncthreads();
     }
 
-    if (groups == 1 || CL > 1) {
+    constexpr bool kWideFits = CL == 1 && groups == 1 &&
+                               (size_t)TPP * 3 * PITCH * (sizeof(float4) + sizeof(float2)) >= (size_t)tasks * kSepKPT * 80;
+    bool wide = false;
+    if constexpr (kWideFits) wide = (a.flags & MUPS_FLAG_WIDE_STORES) && !(a.flags & MUPS_LAYOUT_CHANNEL);
+    if (wide) {
+        // out lives in a peer GPU's memory: 16-byte stores at a 320-byte stride travel badly over NVLink, so the
+        // (query, scale) result is transposed through the (now idle) factor-table region and written as 80-byte runs
+        constexpr int G = tasks * kSepKPT;
+        float4* tile = reinterpret_cast<float4*>(smem_raw);
+        if (tid < tasks) {
+            const int j = tid % ny, i = (tid / ny) % nx, kq = tid / nxy;
+#pragma unroll
+            for (int g = 0; g < kSepKPT; ++g) {
+                const int gi = (i * ny + j) * nz + kq * kSepKPT + g;
+#pragma unroll
+                for (int c = 0; c < 20; c += 4)
+                    tile[gi * 5 + (c >> 2)] = make_float4(v[g][c] * inv_norm[c], v[g][c + 1] * inv_norm[c + 1],
+                                                          v[g][c + 2] * inv_norm[c + 2], v[g][c + 3] * inv_norm[c + 3]);
+            }
+        }
+        __syncthreads();
+        float4* o = reinterpret_cast<float4*>(a.out);
+        for (int f = tid; f < G * 5; f += NT) {
+            const int gi = f / 5, c4 = f - 5 * gi;
+            o[((b * G + gi) * (int64_t)S + s) * 5 + c4] = tile[f];
+        }
+    } else if (groups == 1 || CL > 1) {
         const int task = (CL > 1 ? (int)crank * NT : 0) + tid;
         if (task < tasks) {
             const int j = task % ny, i = (task / ny) % nx, kq = task / nxy;

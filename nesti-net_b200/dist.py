@@ -127,3 +127,54 @@ def bind_to_gpu_numa_node(device_index):
         return True
     except Exception:
         return False
+
+
+# --------------------------------------------------------------------------------------------------
+# gather through peer memory: the statistics kernel's own stores are the collective
+# --------------------------------------------------------------------------------------------------
+
+class PeerSlabGather(object):
+    """Single-rank consumer of the full MuPS tensor without a separate collective.
+
+    Every rank allocates the same symmetric buffer [total_rows, *row_shape]; the rendezvous maps each
+    rank's buffer into every process over NVLink / NVSwitch peer memory.  Rank r then passes
+    ``target(lo, hi)`` -- rows [lo, hi) of the CONSUMER's buffer -- as the ``out`` of its statistics
+    launch: the kernel epilogue's float4 stores travel to the consumer as they are issued, CTA by CTA,
+    overlapped with the arithmetic of the CTAs still running, and nothing is staged locally or re-sent.
+    ``finish()`` (stream sync + a barrier over the signal pads) makes the slabs visible; the consumer
+    reads ``result()``.  Bit-identical to the single-GPU tensor (there is no reduction).
+
+    Uses torch's symmetric-memory allocator (cuMem + peer mapping) for the plumbing; raises
+    RuntimeError where the platform cannot map peer memory between processes."""
+
+    def __init__(self, total_rows, row_shape, dst=0, group=None, device=None, dtype=torch.float32):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerSlabGather needs an initialised process group")
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+        except Exception as e:  # pragma: no cover
+            raise RuntimeError("symmetric memory is not available in this torch build: %s" % (e,))
+        self.group = dist.group.WORLD if group is None else group
+        self.dst = int(dst)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.shape = (int(total_rows),) + tuple(int(x) for x in row_shape)
+        self.dtype = dtype
+        try:
+            self.local = symm_mem.empty(self.shape, dtype=dtype, device=self.device)
+            self.handle = symm_mem.rendezvous(self.local, self.group)
+            self.remote = self.handle.get_buffer(self.dst, self.shape, dtype)
+        except Exception as e:
+            raise RuntimeError("peer-memory rendezvous failed (%s: %s)" % (type(e).__name__, e))
+
+    def target(self, lo, hi):
+        """Rows [lo, hi) of the consumer's buffer, addressable from this rank's kernels."""
+        return self.remote[int(lo):int(hi)]
+
+    def finish(self):
+        """All slabs written before this call on any rank are visible at the consumer after it."""
+        torch.cuda.current_stream(self.device).synchronize()
+        self.handle.barrier()
+
+    def result(self):
+        """The consumer's full tensor (valid after finish()); other ranks get their own, unused buffer."""
+        return self.local

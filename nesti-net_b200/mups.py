@@ -225,12 +225,13 @@ class PointIndex(object):
 # Half 2
 # --------------------------------------------------------------------------------------------------
 
-def stats_3dmfv(patches, n_eff, gmm, n_scales, masked=True, layout="mups", out=None, fastpath=True):
+def stats_3dmfv(patches, n_eff, gmm, n_scales, masked=True, layout="mups", out=None, fastpath=True, wide_stores=False):
     """3DmFV statistics of patches [B, S*P, 3] for all S scales in one launch (mups_3dmfv).
 
     layout 'mups'    -> [B, res, res, res, 20*S] (models/experts_n_est.py:71-76; [B, G, 20*S] when
                         G is not a cube)
     layout 'channel' -> [B, S, 20, G]            (per scale the flatten=True / flatten=False memory order)
+    wide_stores: write each (query, scale) result as 80-byte runs (for `out` in a peer GPU's memory, dist.PeerSlabGather)
     """
     dev = gmm.device
     pts = _as_device(patches, torch.float32, dev)
@@ -250,6 +251,8 @@ def stats_3dmfv(patches, n_eff, gmm, n_scales, masked=True, layout="mups", out=N
         flags |= _lib.FLAG_MASKED
     if not fastpath:
         flags |= _lib.FLAG_NO_FASTPATH
+    if wide_stores:
+        flags |= _lib.FLAG_WIDE_STORES
     if layout == "mups":
         res = int(round(G ** (1.0 / 3.0)))
         shape = (B, res, res, res, 20 * S) if res ** 3 == G else (B, G, 20 * S)

@@ -2,6 +2,7 @@
 oracle on the same seeded inputs, against the committed golden fixtures, and -- at
 BASELINE.json's full sizes -- through size-independent properties."""
 import os
+import socket
 
 import numpy as np
 import pytest
@@ -554,6 +555,47 @@ def test_sharded_slabs_and_host_pipeline():
     assert pipe.features_to_consumer(torch.from_numpy(pts), sub, on_device) == len(sub)
     assert chunks[0] == (0, 1024) and chunks[-1][1] == len(sub)
     assert torch.equal(kept[:len(sub)], full.reshape(n, -1)[torch.from_numpy(sub).cuda()])
+
+
+def test_wide_stores_and_peer_slab_gather():
+    """MUPS_FLAG_WIDE_STORES (results written as 80-byte runs, for `out` in a peer GPU's memory) changes no bit, and
+    dist.PeerSlabGather -- the statistics kernel storing its slab straight into the consumer rank's buffer -- returns
+    the single-GPU tensor (world size 1 here; profiles/bench_peer_gather.py is the 2-GPU run)."""
+    import torch.distributed as dist
+    n, P = 5000, 96
+    radius = [0.04, 0.09]
+    pts = orc.synthetic_cloud(n, cloud_id=21)
+    index = mb.PointIndex(pts, cell_frac=max(radius))
+    radii = index.absolute_radii(radius)
+    q = np.arange(0, n, 2, dtype=np.int64)
+    patches, n_eff, _ = index.ball_query(q, radii, P, seed=SEED)
+    for res, var in ((8, 0.0156), (4, 0.0625), (16, 0.00390625)):
+        w, mu, sg = grid_gmm(res, var)
+        gmm = mb.gmm_handle(w, mu, sg)
+        base = mb.stats_3dmfv(patches, n_eff, gmm, 2)
+        assert torch.equal(mb.stats_3dmfv(patches, n_eff, gmm, 2, wide_stores=True), base), res
+        ch = mb.stats_3dmfv(patches, n_eff, gmm, 2, layout="channel")
+        assert torch.equal(mb.stats_3dmfv(patches, n_eff, gmm, 2, layout="channel", wide_stores=True), ch)
+    w, mu, sg = grid_gmm(8, 0.0156)
+    gmm = mb.gmm_handle(w, mu, sg)
+    full = mb.stats_3dmfv(patches, n_eff, gmm, 2)
+    port = socket.socket()
+    port.bind(("127.0.0.1", 0))
+    addr = "tcp://127.0.0.1:%d" % port.getsockname()[1]
+    port.close()
+    dist.init_process_group("nccl", init_method=addr, rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        try:
+            gather = mb.dist.PeerSlabGather(len(q), (8, 8, 8, 40), dst=0)
+        except RuntimeError as e:
+            pytest.skip("peer memory is not available here: %s" % e)
+        half = len(q) // 2
+        for lo, hi in ((0, half), (half, len(q))):
+            mb.stats_3dmfv(patches[lo:hi], n_eff[lo:hi], gmm, 2, out=gather.target(lo, hi), wide_stores=True)
+        gather.finish()
+        assert torch.equal(gather.result(), full)
+    finally:
+        dist.destroy_process_group()
 
 
 def test_inference_driver(tmp_path):
