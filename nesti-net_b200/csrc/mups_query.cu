@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
     __shared__ uint32_t s_cnt[MUPS_MAX_SCALES], s_nsel[MUPS_MAX_SCALES], s_nb[MUPS_MAX_SCALES];
     __shared__ uint32_t s_prefix[MUPS_MAX_SCALES], s_bits[MUPS_MAX_SCALES], s_need[MUPS_MAX_SCALES];
     __shared__ uint32_t s_min[MUPS_MAX_SCALES], s_max[MUPS_MAX_SCALES];
-    __shared__ uint32_t s_unresolved, s_nhits;
+    __shared__ uint32_t s_unresolved, s_nhits, s_fused;
     __shared__ uint32_t s_warp_sums[kQT / 32];
     __shared__ Salts salt;
 
@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
                 if (lane == 0 && v) atomicAdd(s_cnt + s, v);
             }
         }
+        // latched here: later scans rewrite st.first_total (with the same value) without a barrier in between
+        if (tid == 0) s_fused = st.first_total > a.fuse ? 1u : 0u;
     }
     __syncthreads();
     const uint32_t nhits = s_nhits;
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
         }
     };
 
-    const bool fused_hist = st.first_total > a.fuse;   // uniform: written once per scan, read after barriers
+    const bool fused_hist = s_fused != 0u;               // uniform
     if (over) {
         // ---- first-level key histogram of the over-full radii ------------------------------------------
         if (!fused_hist) visit(over, [&](uint32_t, uint32_t idx, uint32_t in) {
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(kQT) ball_query_kernel(const QueryArgs a) {
                 const uint32_t nb = min((uint32_t)kBinBits, 32u - bits);
                 uint32_t T, below, group;
                 warp_find_threshold(hist + warp * kBins, 1 << nb, s_need[warp], lane, &T, &below, &group);
+                __syncwarp();                 // every lane has read s_bits / s_need before lane 0 updates them
                 if (lane == 0) {
                     s_prefix[warp] = (s_prefix[warp] << nb) | T; s_bits[warp] = bits + nb; s_need[warp] -= below;
                     // with all 32 key bits fixed the group is a set of exact key ties; more than the cap of
