@@ -111,6 +111,52 @@ def make_half1():
     np.savez_compressed(os.path.join(HERE, "half1_reference.npz"), **flat)
 
 
+def make_dataset_interface():
+    """The dataset interface around half 1, run on the unmodified reference: two shapes, sparse patch centres (.pidx),
+    targets 'normal' / 'max_curvature' / 'min_curvature' (pcpnet_dataset.py:292-295, 345-352, 405-417), global index ->
+    (shape, patch) mapping (:427-436)."""
+    sys.path.insert(0, REF_UTILS)
+    import pcpnet_dataset as ref
+    rng = np.random.RandomState(31)
+    radii, P = [0.04, 0.1], 32
+    out = {"patch_radius": np.asarray(radii, np.float64), "P": np.int64(P)}
+    with tempfile.TemporaryDirectory() as d:
+        names = ["shape_a", "shape_b"]
+        for k, name in enumerate(names):
+            n = 2500 + 700 * k
+            pts = orc.synthetic_cloud(n, cloud_id=40 + k, noise=0.001)
+            nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+            curv = rng.uniform(-2, 2, size=(n, 2))
+            pidx = np.sort(rng.choice(n, 40 + 10 * k, replace=False))
+            np.savetxt(os.path.join(d, name + ".xyz"), pts, fmt="%.9g")
+            np.savetxt(os.path.join(d, name + ".normals"), nrm.astype(np.float32), fmt="%.9g")
+            np.savetxt(os.path.join(d, name + ".curv"), curv.astype(np.float32), fmt="%.9g")
+            np.savetxt(os.path.join(d, name + ".pidx"), pidx, fmt="%d")
+            out.update({name + "_pts": pts, name + "_normals": nrm.astype(np.float32), name + "_curv": curv.astype(np.float32),
+                        name + "_pidx": pidx.astype(np.int64)})
+        with open(os.path.join(d, "list.txt"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        ds = ref.PointcloudPatchDataset(
+            root=d, shape_list_filename="list.txt", patch_radius=radii, points_per_patch=P,
+            patch_features=["normal", "max_curvature", "min_curvature"], seed=3627473, identical_epochs=False,
+            use_pca=False, center="point", point_tuple=1, cache_capacity=100, point_count_std=0, sparse_patches=True)
+        out["shape_patch_count"] = np.asarray(ds.shape_patch_count, np.int64)
+        out["patch_radius_absolute"] = np.asarray(ds.patch_radius_absolute, np.float64)
+        out["length"] = np.int64(len(ds))
+        idx = np.asarray([0, 1, 17, 39, 40, 41, 63, 89], np.int64)        # both shapes, both ends
+        items = [ds[int(i)] for i in idx]
+        out["item_index"] = idx
+        out["item_shape_index"] = np.asarray([ds.shape_index(int(i)) for i in idx], np.int64)
+        out["item_normal"] = np.stack([it[1].numpy() for it in items])
+        out["item_max_curv"] = np.stack([it[2].numpy() for it in items])
+        out["item_min_curv"] = np.stack([it[3].numpy() for it in items])
+        out["item_trans"] = np.stack([it[4].numpy() for it in items])
+        out["item_n_eff"] = np.stack([np.asarray(it[5], np.float64) for it in items])
+        print("dataset interface: len", len(ds), "counts", ds.shape_patch_count, "dtypes",
+              items[0][1].dtype, items[0][2].dtype, np.asarray(items[0][5]).dtype)
+    np.savez_compressed(os.path.join(HERE, "dataset_reference.npz"), **out)
+
+
 def make_half2():
     rng = np.random.RandomState(11)
     out = {}
@@ -272,6 +318,7 @@ def make_rotation_reference():
 
 if __name__ == "__main__":
     make_half1()
+    make_dataset_interface()
     make_half2_reference_numpy()
     make_rotation_reference()
     make_half2()

@@ -454,6 +454,44 @@ def test_dataset_drop_in(tmp_path, half1):
     assert ds_same.epoch == 0 and ds_same.selection_seed() == SEED
 
 
+def test_dataset_interface_against_reference_run(tmp_path, golden_dir):
+    """Two shapes, sparse patch centres (.pidx), normal / curvature targets, global index -> (shape, patch): the mirror
+    against outputs of the unmodified reference dataset (tests/golden/make_golden.py::make_dataset_interface)."""
+    ref = np.load(os.path.join(golden_dir, "dataset_reference.npz"))
+    radius, P = list(ref["patch_radius"]), int(ref["P"])
+    names = ["shape_a", "shape_b"]
+    for name in names:
+        np.savetxt(tmp_path / (name + ".xyz"), ref[name + "_pts"], fmt="%.9g")
+        np.savetxt(tmp_path / (name + ".normals"), ref[name + "_normals"], fmt="%.9g")
+        np.savetxt(tmp_path / (name + ".curv"), ref[name + "_curv"], fmt="%.9g")
+        np.savetxt(tmp_path / (name + ".pidx"), ref[name + "_pidx"], fmt="%d")
+    (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
+    ds = mb.pcpnet_dataset.PointcloudPatchDataset(
+        root=str(tmp_path), shape_list_filename="list.txt", patch_radius=radius, points_per_patch=P,
+        patch_features=["normal", "max_curvature", "min_curvature"], seed=SEED, identical_epochs=False,
+        use_pca=False, center="point", point_tuple=1, cache_capacity=100, point_count_std=0, sparse_patches=True)
+    assert ds.shape_patch_count == list(ref["shape_patch_count"]) and len(ds) == int(ref["length"])
+    assert np.array_equal(np.asarray(ds.patch_radius_absolute, np.float64), ref["patch_radius_absolute"])
+    for k, gi in enumerate(ref["item_index"]):
+        assert tuple(ds.shape_index(int(gi))) == tuple(ref["item_shape_index"][k])
+        patch_pts, normal, cmax, cmin, trans, ne = ds[int(gi)]
+        assert normal.dtype == torch.float32 and np.array_equal(normal.numpy(), ref["item_normal"][k])
+        assert cmax.dtype == torch.float32 and np.array_equal(cmax.numpy(), ref["item_max_curv"][k])
+        assert np.array_equal(cmin.numpy(), ref["item_min_curv"][k])
+        assert np.array_equal(trans.numpy(), ref["item_trans"][k])
+        assert np.asarray(ne).dtype == np.float64 and np.array_equal(ne, ref["item_n_eff"][k])
+        # the patch itself against the oracle at the sparse centre
+        shape_ind, patch_ind = ref["item_shape_index"][k]
+        centre = int(ref[names[shape_ind] + "_pidx"][patch_ind])
+        o_p, o_ne, _ = orc.gather_patches(ref[names[shape_ind] + "_pts"], np.array([centre]), radius, P, seed=SEED)
+        assert np.array_equal(patch_pts.numpy(), o_p[0]) and np.array_equal(ne, o_ne[0].astype(np.float64))
+    with pytest.raises(IndexError):
+        ds.shape_index(len(ds))
+    batch = ds.get_batch([0, 41, 89])                     # one call across both shapes
+    assert np.array_equal(batch[1].numpy(), ref["item_normal"][[0, 5, 7]])
+    assert np.array_equal(batch[-1].cpu().numpy(), ref["item_n_eff"][[0, 5, 7]])
+
+
 def test_full_size_properties():
     """BASELINE configs[1] shape (100k-point cloud, 4 scales, P=512, 8^3 grid): size-independent
     properties on 8192 of the queries + oracle spot check."""
