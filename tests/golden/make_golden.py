@@ -157,6 +157,62 @@ def make_dataset_interface():
     np.savez_compressed(os.path.join(HERE, "dataset_reference.npz"), **out)
 
 
+def make_evaluation_reference():
+    """utils/evaluate.py run as the script it is (runpy) on synthetic predictions: per-shape unoriented RMS angle,
+    PGP5, PGP10 and the shape averages, parsed from the summary it writes.  `visualization` and `utils` (matplotlib /
+    h5py importers, used only under EXPORT) are satisfied with empty shims; the evaluation code itself is untouched."""
+    import ast
+    import runpy
+    import types
+    rng = np.random.RandomState(17)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        data, res = os.path.join(d, "data") + os.sep, os.path.join(d, "run", "results") + os.sep
+        os.makedirs(data)
+        os.makedirs(res)
+        names = ["s0", "s1", "s2"]
+        for k, name in enumerate(names):
+            n = 400 + 50 * k
+            pts = rng.normal(size=(n, 3)).astype(np.float32)
+            gt = rng.normal(size=(n, 3)); gt /= np.linalg.norm(gt, axis=1, keepdims=True)
+            pidx = np.sort(rng.choice(n, 120, replace=False))
+            # predictions: the ground truth perturbed by 1..25 degrees, random sign (unoriented), not normalised
+            pert = gt + rng.normal(size=(n, 3)) * rng.uniform(0.02, 0.45, size=(n, 1))
+            pred_full = pert * rng.choice([-1.0, 1.0], size=(n, 1)) * rng.uniform(0.5, 2.0, size=(n, 1))
+            pred = pred_full[pidx] if k != 1 else pred_full          # shape s1: dense predictions, subset by .pidx
+            np.savetxt(data + name + ".xyz", pts, fmt="%.9g")
+            np.savetxt(data + name + ".normals", gt.astype(np.float32), fmt="%.9g")
+            np.savetxt(data + name + ".pidx", pidx, fmt="%d")
+            np.savetxt(res + name + ".normals", pred.astype(np.float32), fmt="%.9g")
+            out.update({name + "_gt": gt.astype(np.float32), name + "_pred": pred.astype(np.float32), name + "_pidx": pidx.astype(np.int64)})
+        with open(data + "evalset.txt", "w") as f:
+            f.write("\n".join(names) + "\n")
+        for mod in ("visualization", "utils"):
+            sys.modules[mod] = types.ModuleType(mod)
+        argv = sys.argv
+        sys.argv = ["evaluate.py", "--normal_results_path", res, "--data_path", data, "--dataset_list", "evalset"]
+        try:
+            runpy.run_path(os.path.join(REF_UTILS, "evaluate.py"), run_name="__main__")
+        finally:
+            sys.argv = argv
+            for mod in ("visualization", "utils"):
+                sys.modules.pop(mod, None)
+        with open(os.path.join(res, "summary", "evalset_evaluation_results.txt")) as f:
+            lines = dict(line.strip().split(": ", 1) for line in f if ": " in line)
+    def parse(v):
+        return np.asarray(eval(v, {"__builtins__": {}}, {"np": np, "float32": np.float32, "float64": np.float64}), np.float64)
+    out["rms"] = parse(lines["RMS per shape"])
+    out["pgp10"] = parse(lines["PGP10 per shape"])
+    out["pgp5"] = parse(lines["PGP5 per shape"])
+    out["avg_rms"] = parse(lines["RMS not oriented (shape average)"])
+    out["avg_rms_o"] = parse(lines["RMS oriented (shape average)"])
+    out["avg_pgp10"] = parse(lines["PGP10 average"])
+    out["avg_pgp5"] = parse(lines["PGP5 average"])
+    out["names"] = np.asarray(names)
+    print("evaluation reference:", {k: out[k] for k in ("rms", "pgp5", "pgp10", "avg_rms_o")})
+    np.savez_compressed(os.path.join(HERE, "evaluation_reference.npz"), **out)
+
+
 def make_half2():
     rng = np.random.RandomState(11)
     out = {}
@@ -319,6 +375,7 @@ def make_rotation_reference():
 if __name__ == "__main__":
     make_half1()
     make_dataset_interface()
+    make_evaluation_reference()
     make_half2_reference_numpy()
     make_rotation_reference()
     make_half2()

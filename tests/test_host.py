@@ -199,6 +199,23 @@ def test_rotation_augmentation_matches_reference_run(golden_dir):
     assert np.array_equal(R2, mb.provider.euler2mat(z=a[0], y=a[1], x=a[2]).T)
 
 
+def test_evaluation_metrics_against_reference_run(golden_dir):
+    """RMS / PGP5 / PGP10 of utils/evaluate.py, run as a script on synthetic predictions by make_golden.py
+    (sparse and dense prediction files, unnormalised and sign-flipped normals): the mirror gives the same numbers
+    (the reference evaluates in float32, the mirror in float64)."""
+    ref = np.load(os.path.join(golden_dir, "evaluation_reference.npz"))
+    recs = []
+    for k, name in enumerate(ref["names"]):
+        recs.append(mb.evaluate.evaluate_shape(ref[name + "_pred"], ref[name + "_gt"], ref[name + "_pidx"]))
+        assert abs(recs[-1]["rms"] - ref["rms"][k]) < 2e-4 * ref["rms"][k]
+        assert recs[-1]["pgp5"] == pytest.approx(ref["pgp5"][k], abs=1e-12)
+        assert recs[-1]["pgp10"] == pytest.approx(ref["pgp10"][k], abs=1e-12)
+        assert recs[-1]["n"] == 120
+    assert abs(np.mean([r["rms"] for r in recs]) - ref["avg_rms"]) < 2e-4 * ref["avg_rms"]
+    assert abs(np.mean([r["rms_o"] for r in recs]) - ref["avg_rms_o"]) < 2e-4 * ref["avg_rms_o"]
+    assert np.mean([r["pgp10"] for r in recs]) == pytest.approx(float(ref["avg_pgp10"]), abs=1e-12)
+
+
 def test_evaluation_metrics():
     """RMS angle / PGP5 / PGP10 as defined in the reference's utils/evaluate.py:133-154."""
     ev = mb.evaluate
