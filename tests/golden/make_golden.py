@@ -157,6 +157,30 @@ def make_dataset_interface():
     np.savez_compressed(os.path.join(HERE, "dataset_reference.npz"), **out)
 
 
+def make_sampler_reference():
+    """Index sequences of the reference's three samplers (pcpnet_dataset.py:41-138) over two epochs."""
+    sys.path.insert(0, REF_UTILS)
+    import pcpnet_dataset as ref
+
+    class DS(object):
+        shape_names = ["a", "b", "c", "d"]
+        shape_patch_count = [10, 5, 20, 7]
+    ds = DS()
+    out = {"shape_patch_count": np.asarray(ds.shape_patch_count, np.int64)}
+    out["sequential"] = np.asarray(list(ref.SequentialPointcloudPatchSampler(ds)), np.int64)
+    for ident in (False, True):
+        r = ref.RandomPointcloudPatchSampler(ds, patches_per_shape=8, seed=3627473, identical_epochs=ident)
+        out["random_ident%d" % ident] = np.asarray([list(r), list(r)], np.int64)
+        for seq_shapes in (False, True):
+            q = ref.SequentialShapeRandomPointcloudPatchSampler(ds, 8, seed=3627473, sequential_shapes=seq_shapes,
+                                                                identical_epochs=ident)
+            out["shape_random_ident%d_seq%d" % (ident, seq_shapes)] = np.asarray([list(q), list(q)], np.int64)
+            out["shape_random_ident%d_seq%d_local" % (ident, seq_shapes)] = np.concatenate(
+                [np.asarray(v, np.int64) for v in q.shape_patch_inds])
+    np.savez_compressed(os.path.join(HERE, "sampler_reference.npz"), **out)
+    print("sampler reference:", {k: v.shape for k, v in out.items()})
+
+
 def make_evaluation_reference():
     """utils/evaluate.py run as the script it is (runpy) on synthetic predictions: per-shape unoriented RMS angle,
     PGP5, PGP10 and the shape averages, parsed from the summary it writes.  `visualization` and `utils` (matplotlib /
@@ -375,6 +399,7 @@ def make_rotation_reference():
 if __name__ == "__main__":
     make_half1()
     make_dataset_interface()
+    make_sampler_reference()
     make_evaluation_reference()
     make_half2_reference_numpy()
     make_rotation_reference()

@@ -169,6 +169,27 @@ def test_samplers():
     assert len(idx) == 21 and all(i < 10 for i in idx[:8]) and all(10 <= i < 15 for i in idx[8:13]) and all(i >= 15 for i in idx[13:])
 
 
+def test_samplers_against_reference_run(golden_dir):
+    """Same index sequences as the reference's samplers (two epochs each, with and without identical_epochs)."""
+    ref = np.load(os.path.join(golden_dir, "sampler_reference.npz"))
+
+    class DS(object):
+        shape_names = ["a", "b", "c", "d"]
+        shape_patch_count = [int(c) for c in ref["shape_patch_count"]]
+    ds = DS()
+    P = mb.pcpnet_dataset
+    assert np.array_equal(list(P.SequentialPointcloudPatchSampler(ds)), ref["sequential"])
+    for ident in (False, True):
+        r = P.RandomPointcloudPatchSampler(ds, patches_per_shape=8, seed=3627473, identical_epochs=ident)
+        assert np.array_equal([list(r), list(r)], ref["random_ident%d" % ident])
+        for seq_shapes in (False, True):
+            q = P.SequentialShapeRandomPointcloudPatchSampler(ds, 8, seed=3627473, sequential_shapes=seq_shapes,
+                                                              identical_epochs=ident)
+            assert np.array_equal([list(q), list(q)], ref["shape_random_ident%d_seq%d" % (ident, seq_shapes)])
+            assert np.array_equal(np.concatenate([np.asarray(v, np.int64) for v in q.shape_patch_inds]),
+                                  ref["shape_random_ident%d_seq%d_local" % (ident, seq_shapes)])
+
+
 def test_dataset_rejects_options_off_the_hot_path(tmp_path):
     (tmp_path / "list.txt").write_text("cloud\n")
     kw = dict(root=str(tmp_path), shape_list_filename="list.txt", patch_radius=[0.05], points_per_patch=16,
