@@ -186,7 +186,7 @@ class PointIndex(object):
     def absolute_radii(self, patch_radius):
         """[bbdiag * rad for rad in patch_radius] (pcpnet_dataset.py:282), Python floats."""
         bbdiag = self.bbdiag()
-        return [bbdiag * rad for rad in patch_radius]
+        return [bbdiag * float(rad) for rad in patch_radius]
 
     def ball_query(self, query_idx, radii_abs, points_per_patch, seed=3627473, return_indices=False,
                    return_patches=True):

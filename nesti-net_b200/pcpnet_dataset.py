@@ -138,7 +138,7 @@ class PointcloudPatchDataset(torch.utils.data.Dataset):
         self.root = root
         self.shape_list_filename = shape_list_filename
         self.patch_features = list(patch_features)
-        self.patch_radius = list(patch_radius)
+        self.patch_radius = [float(r) for r in patch_radius]      # Python floats, as argparse hands them to the reference
         self.points_per_patch = int(points_per_patch)
         self.identical_epochs = identical_epochs
         self.use_pca = use_pca
