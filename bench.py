@@ -411,6 +411,35 @@ def run_own(args):
                 "peak_is": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"},
         "traffic": None,
     }
+    # the second kernel of the step, timed alone (inside the loop it runs on the side stream under the statistics
+    # kernel): algorithmic bytes = 16 B per true neighbour visited + the patches and counts written;
+    # the 2.9 MB index of a 100 k-point cloud is L2-resident, so this is an L2/latency figure, not an HBM one
+    torch.cuda.synchronize()
+    bq_index = mb.PointIndex(clouds_dev[0], cell_frac=max(RADIUS))
+    bq_radii = np.ascontiguousarray(bq_index.absolute_radii(RADIUS), dtype=np.float64)
+
+    def bq_launch():
+        _lib.check(L.mups_ball_query(bq_index.handle, ctypes.c_void_p(q_shard.data_ptr()), per_cloud,
+                                     bq_radii.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), S, P, SEED, None,
+                                     ctypes.c_void_p(total[:per_cloud].data_ptr()), ctypes.c_void_p(patches[:per_cloud].data_ptr()),
+                                     ctypes.c_void_p(n_eff[:per_cloud].data_ptr()), sptr))
+    for _ in range(2):
+        bq_launch()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for _ in range(5):
+        bq_launch()
+    b1.record(stream)
+    torch.cuda.synchronize()
+    bq_ms = b0.elapsed_time(b1) / 5
+    nbrs = float(total[:per_cloud].sum().item())
+    bq_bytes = 16.0 * nbrs + per_cloud * (12.0 * S * P + 8.0 * S)
+    roofline["ball_query"] = {"kernel": "ball_query_kernel (K3+K4), timed alone", "ms_per_launch": bq_ms,
+                              "queries_per_launch": per_cloud, "mean_neighbours_per_query": nbrs / per_cloud,
+                              "algorithmic_GBps": bq_bytes / (bq_ms * 1e-3) / 1e9, "hbm_peak_GBps": hbm_peak,
+                              "frac_of_hbm_peak": bq_bytes / (bq_ms * 1e-3) / 1e9 / hbm_peak,
+                              "note": "index is L2-resident at this cloud size; latency/barrier bound (profiles/r01_ball_query.md)"}
+    del bq_index
     prof = os.path.join(ROOT, "profiles", "stats_kernel_traffic.json")
     if os.path.exists(prof):
         try:
