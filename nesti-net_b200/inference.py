@@ -31,6 +31,8 @@ def estimate_normals(indir, dataset_name, outdir, model, gmm, patch_radius, poin
     handle = _m.gmm_handle(gmm.weights_, gmm.means_, np.sqrt(gmm.covariances_))
     model_device = next(model.parameters()).device
     model.eval()
+    if model_device.type == "cuda":
+        torch.backends.cudnn.benchmark = True      # the 8^3 conv3d stack is 2-3x faster with cuDNN's tuned algorithms
     n_rads = len(patch_radius)
     normals, experts, probs = [], [], []
     for data in loader:

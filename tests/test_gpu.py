@@ -671,8 +671,8 @@ def test_inference_driver(tmp_path):
 def test_downstream_moe_normals():
     """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
     models/experts_n_est.py, fp32) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4 angular
-    RMS (degrees, the unit of utils/evaluate.py).  The network runs on the host: it is the checker here, and
-    cuDNN's strict-fp32 conv3d path on 8^3 volumes is two orders of magnitude slower than the CPU."""
+    RMS (degrees, the unit of utils/evaluate.py).  The network runs on the host in strict fp32: it is the checker
+    here (profiles/bench_moe.py measures it on the GPU)."""
     from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg
     pts = orc.synthetic_cloud(30000, cloud_id=9, noise=0.001)
     radius = [0.01, 0.03, 0.05, 0.07]
