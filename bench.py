@@ -533,8 +533,27 @@ def run_own(args):
         c0 = time.perf_counter()
         done = cpu_reference_pass(clouds_host[0], tree, cpu_sample_queries(1, sample), feed)
         cdt = time.perf_counter() - c0
+        # the reference as its scripts run it: one process, one kd-tree query per patch and scale,
+        # the un-fused op chain of get_3dmfv_n_est (numpy transliteration) -- a small sample, reported next to the
+        # all-core figure
+        shipped = None
+        if "cpu" not in skip:
+            qs = cpu_sample_queries(2, 16)
+            s0 = time.perf_counter()
+            rads_ = orc.absolute_radii(clouds_host[0], RADIUS)
+            pp = np.zeros((len(qs), S * P, 3), np.float32)
+            ne_ = np.zeros((len(qs), S), np.int32)
+            for b_, c_ in enumerate(qs):
+                for s_, rad_ in enumerate(rads_):
+                    inds_ = np.asarray(tree.query_ball_point(clouds_host[0][c_], rad_), np.int64)
+                    ne_[b_, s_] = min(P, len(inds_))
+                    inds_ = orc.select_subset(inds_, P, SEED, int(c_), s_)
+                    pp[b_, s_ * P: s_ * P + len(inds_)] = (clouds_host[0][inds_] - clouds_host[0][c_]) / np.float32(rad_)
+            orc.mups_assemble(pp, feed[0], feed[1], feed[2], ne_, S)
+            sdt = time.perf_counter() - s0
+            shipped = {"value": len(qs) / sdt, "unit": UNIT, "cores": 1, "sample": "%d query points, one process" % len(qs)}
         cpu_baseline = {"value": done / cdt, "unit": UNIT, "cores": os.cpu_count(), "threads_half2": c_oracle.num_threads(),
-                        "kind": "port",
+                        "kind": "port", "as_shipped_one_process": shipped,
                         "sample": "%d strided query points of cloud 0 (kd-tree build excluded); cKDTree.query_ball_point("
                                   "workers=-1) + oracle C port (OpenMP) of get_3dmfv_n_est" % sample}
     if rank == 0:
