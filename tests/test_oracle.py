@@ -173,6 +173,39 @@ def test_half2_posterior_stage_pinned_by_reference(half2_ref, case):
     assert frac_outside(got2, ref) == 0.0
 
 
+def test_half2_properties():
+    """Size-independent properties of the statistics the CUDA tests rely on at full size: invariance to the order of
+    the unmasked points, every channel L2-normalised over the Gaussians (or identically zero), max channels >= min
+    channels, and invariance of the normalised features to the positive factors that cancel in the channel norm
+    (n_eff = P - 1 vs P masks nothing, tf_util.py:696)."""
+    from hypothesis import given, settings, strategies as st
+
+    w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([4] * 3, 0.0625))
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(st.integers(1, 24), st.integers(0, 2 ** 31 - 1))
+    def check(ne, seed):
+        rng = np.random.RandomState(seed)
+        P = 24
+        pts = np.zeros((1, P, 3), np.float32)
+        x = rng.normal(size=(ne, 3)) * rng.uniform(0.05, 0.6)
+        x /= np.maximum(1.0, np.linalg.norm(x, axis=1, keepdims=True))
+        pts[0, :ne] = x
+        fv = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False, n_original_points=[ne])[0]        # [20, G]
+        perm = rng.permutation(ne)
+        p2 = pts.copy()
+        p2[0, :ne] = pts[0, :ne][perm]
+        fv2 = orc.get_3dmfv_n_est(p2, w, mu, sg, flatten=False, n_original_points=[ne])[0]
+        assert np.abs(fv - fv2).max() < 2e-6                                   # only the sums re-associate
+        nrm = np.sqrt((fv.astype(np.float64) ** 2).sum(-1))
+        assert np.all((np.abs(nrm - 1) < 1e-5) | (nrm == 0))
+        # max >= min holds before the per-channel normalisation; after it the signs still cannot cross
+        assert not np.any((fv[2:5] < 0) & (fv[5:8] > 0)) and not np.any((fv[11:14] < 0) & (fv[14:17] > 0))
+        if ne < P - 1:      # masked slots feed exact zeros into max / min (tf_util.py:698,703)
+            assert np.all(fv[[0, 2, 3, 4, 11, 12, 13]] >= 0) and np.all(fv[[5, 6, 7, 14, 15, 16]] <= 0)
+    check()
+
+
 def test_mask_off_by_one_and_padding_semantics():
     """tf_util.py:696 masks r > n_eff: slot n_eff (a zero pad) takes part, slot n_eff+1 does not;
     masked slots feed exact zeros into max/min."""
