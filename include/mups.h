@@ -76,7 +76,11 @@ int64_t mups_launch_count(void);
  * "fuse_candidates" (default 12288): candidate points in a ball's first cell batch above which the
  * first scan also builds the subsample's key histograms (dense balls; results never depend on it).
  * "stats_variant" (0 = automatic; 1 round-1 loop and staging, 2 all-scalar loop, 8 no cluster at 16^3):
- * force a statistics-kernel variant (benchmarking only). */
+ * force a statistics-kernel variant (benchmarking only).
+ * "query_kernel" (0 = automatic: hierarchical for indices with >= 6 Morton bits per axis, i.e. fine grids; 1 = flat
+ * cell scan; 2 = hierarchical), "query_order" (0 = automatic; 1 = CTAs in caller order; 2 = CTAs in Morton order of the
+ * centres) and "hier_margin" (-1 = automatic; extra expected candidates above P kept by the hierarchical kernel's key
+ * threshold; tests set 0 to exercise the hand-over to the flat kernel): results never depend on any of them. */
 int mups_set_option(const char* name, int64_t value);
 
 /* ---- spatial index (K1 bbox + K2 grid build) --------------------------------------------- */

@@ -14,6 +14,9 @@ std::atomic<int64_t> g_launch_count{0};
 std::atomic<int> g_boundary_cap{512};
 std::atomic<int> g_fuse_candidates{3 * 4096};
 std::atomic<int> g_stats_variant{0};
+std::atomic<int> g_query_kernel{0};
+std::atomic<int> g_query_order{0};
+std::atomic<int> g_hier_margin{-1};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -93,6 +96,21 @@ int mups_set_option(const char* name, int64_t value) {
         g_stats_variant.store((int)value);
         return MUPS_OK;
     }
+    if (!strcmp(name, "query_kernel")) {
+        MUPS_REQUIRE(value >= 0 && value <= 2, "mups_set_option: query_kernel=%lld out of range [0, 2]", (long long)value);
+        g_query_kernel.store((int)value);
+        return MUPS_OK;
+    }
+    if (!strcmp(name, "hier_margin")) {
+        MUPS_REQUIRE(value >= -1 && value <= 4096, "mups_set_option: hier_margin=%lld out of range [-1, 4096]", (long long)value);
+        g_hier_margin.store((int)value);
+        return MUPS_OK;
+    }
+    if (!strcmp(name, "query_order")) {
+        MUPS_REQUIRE(value >= 0 && value <= 2, "mups_set_option: query_order=%lld out of range [0, 2]", (long long)value);
+        g_query_order.store((int)value);
+        return MUPS_OK;
+    }
     set_error("mups_set_option: unknown option '%s'", name);
     return MUPS_ERR_INVALID;
 }
@@ -115,6 +133,7 @@ void mups_index_destroy(mups_index* ix) {
     if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->build_stream);
     if (ix->pos_of) cudaFreeAsync(ix->pos_of, ix->build_stream);
     if (ix->codes) cudaFreeAsync(ix->codes, ix->build_stream);
+    if (ix->idx_sorted) cudaFreeAsync(ix->idx_sorted, ix->build_stream);
     if (prev >= 0) cudaSetDevice(prev);
     delete ix;
 }
@@ -163,6 +182,7 @@ int mups_index_create(mups_index** out, const float* xyz_dev, int64_t n, double 
     if ((rc = alloc((void**)&ix->cell_start, sizeof(uint32_t) * (size_t)(n_scan + n_tiles + 8)))) return fail(rc);
     if ((rc = alloc((void**)&ix->pos_of, sizeof(int32_t) * (size_t)n))) return fail(rc);
     if ((rc = alloc((void**)&ix->codes, sizeof(uint32_t) * (size_t)(n < 8 ? 8 : n)))) return fail(rc);
+    if ((rc = alloc((void**)&ix->idx_sorted, sizeof(int32_t) * (size_t)n))) return fail(rc);
     ix->build_stream = st;
     if ((rc = launch_index_build(ix, xyz_dev, st))) return fail(rc);
     if (cudaEventCreateWithFlags(&ix->built, cudaEventDisableTiming) != cudaSuccess ||
@@ -207,7 +227,7 @@ int mups_ball_query(const mups_index* ix, const int64_t* query_idx_dev, int64_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (st != ix->build_stream) MUPS_CUDA_TRY(cudaStreamWaitEvent(st, ix->built, 0));
     if (int rc = launch_ball_query(ix, query_idx_dev, B, r_abs_host, S, P, seed, nbr_idx_dev, nbr_total_dev, patches_dev,
-                                   n_eff_dev, st))
+                                   n_eff_dev, nullptr, st))
         return rc;
     return note_use(ix, st);
 }

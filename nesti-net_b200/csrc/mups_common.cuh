@@ -23,6 +23,9 @@ extern std::atomic<int64_t> g_launch_count;
 extern std::atomic<int> g_boundary_cap;
 extern std::atomic<int> g_fuse_candidates;
 extern std::atomic<int> g_stats_variant;
+extern std::atomic<int> g_query_kernel;     // 0 automatic, 1 flat cell scan, 2 hierarchical (octree over the Morton codes)
+extern std::atomic<int> g_hier_margin;      // -1 automatic (6 sqrt(P) + 8); tests set 0 to exercise the worklist hand-over
+extern std::atomic<int> g_query_order;      // 0 automatic, 1 CTAs in caller order, 2 CTAs in Morton order of the centres
 
 #define MUPS_CUDA_TRY(expr)                                                                   \
     do {                                                                                      \
@@ -73,6 +76,8 @@ struct mups_index {
     uint32_t* cell_start = nullptr;      // device [ncode + 1]: exclusive prefix of cell populations
     int32_t* pos_of = nullptr;           // device [n]: position in `sorted` of original point i
     uint32_t* codes = nullptr;           // device [n]: Morton cell code per original point (build scratch, kept)
+    int32_t* idx_sorted = nullptr;       // device [n]: original index of sorted[i] alone (4 B/point: the hierarchical
+                                         // query reads only this for cells wholly inside a ball)
     cudaStream_t build_stream = nullptr;
     cudaEvent_t built = nullptr;
     // host copy of the bbox, fetched lazily by mups_index_bbox
@@ -109,7 +114,9 @@ int library_pool(int device, cudaMemPool_t* pool);
 int launch_index_build(mups_index* ix, const float* xyz, cudaStream_t st);
 int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const double* r_abs, int S, int P,
                       uint64_t seed, int32_t* nbr_idx, int32_t* nbr_total, float* patches, int32_t* n_eff,
-                      cudaStream_t st);
+                      int32_t* nbr_pos, cudaStream_t st);
+// in-place exclusive scan of n uint32 counters; tile_sums: scratch of (n + 2047) / 2048 entries
+int launch_exclusive_scan(uint32_t* data, int64_t n, uint32_t* tile_sums, cudaStream_t st);
 int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff, int64_t B, int S, int P,
                  uint32_t flags, float* out, int* work, cudaStream_t st);
 
@@ -124,6 +131,14 @@ __device__ __forceinline__ uint32_t morton_expand(uint32_t v) {  // 10 bits -> e
 }
 __device__ __forceinline__ uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
     return morton_expand(x) | (morton_expand(y) << 1) | (morton_expand(z) << 2);
+}
+__device__ __forceinline__ uint32_t morton_compact(uint32_t v) {  // every third bit -> 10 bits
+    v &= 0x09249249u;
+    v = (v | (v >> 2)) & 0x030C30C3u;
+    v = (v | (v >> 4)) & 0x0300F00Fu;
+    v = (v | (v >> 8)) & 0x030000FFu;
+    v = (v | (v >> 16)) & 0x3FFu;
+    return v;
 }
 __device__ __forceinline__ int cell_coord(float p, float origin, float inv_cell, int dim) {
     int c = (int)floorf((p - origin) * inv_cell);

@@ -168,13 +168,25 @@ __global__ void __launch_bounds__(256) scatter_kernel(const float* __restrict__ 
                                                       const uint32_t* __restrict__ codes,
                                                       const uint32_t* __restrict__ cell_start,
                                                       int32_t* __restrict__ pos_of /* in: rank, out: position */,
-                                                      float4* __restrict__ sorted) {
+                                                      float4* __restrict__ sorted, int32_t* __restrict__ idx_sorted) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t pos = (int32_t)(cell_start[codes[i]] + (uint32_t)pos_of[i]);
         pos_of[i] = pos;
         sorted[pos] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2),
                                   __int_as_float((int)i));
+        idx_sorted[pos] = (int32_t)i;
     }
+}
+
+int launch_exclusive_scan(uint32_t* data, int64_t n, uint32_t* tile_sums, cudaStream_t st) {
+    const int n_tiles = (int)((n + kScanTile - 1) / kScanTile);
+    scan_tile_sums_kernel<<<n_tiles, kScanThreads, 0, st>>>(data, n, tile_sums);
+    MUPS_CHECK_LAUNCH();
+    scan_spine_kernel<<<1, kScanThreads, 0, st>>>(tile_sums, n_tiles);
+    MUPS_CHECK_LAUNCH();
+    scan_apply_kernel<<<n_tiles, kScanThreads, 0, st>>>(data, n, tile_sums);
+    MUPS_CHECK_LAUNCH();
+    return MUPS_OK;
 }
 
 int launch_index_build(mups_index* ix, const float* xyz, cudaStream_t st) {
@@ -196,16 +208,10 @@ int launch_index_build(mups_index* ix, const float* xyz, cudaStream_t st) {
     MUPS_CHECK_LAUNCH();
 
     const int64_t n_scan = ncode + 1;
-    const int n_tiles = (int)((n_scan + kScanTile - 1) / kScanTile);
     uint32_t* tile_sums = ix->cell_start + n_scan;            // allocated with n_tiles extra entries
-    scan_tile_sums_kernel<<<n_tiles, kScanThreads, 0, st>>>(ix->cell_start, n_scan, tile_sums);
-    MUPS_CHECK_LAUNCH();
-    scan_spine_kernel<<<1, kScanThreads, 0, st>>>(tile_sums, n_tiles);
-    MUPS_CHECK_LAUNCH();
-    scan_apply_kernel<<<n_tiles, kScanThreads, 0, st>>>(ix->cell_start, n_scan, tile_sums);
-    MUPS_CHECK_LAUNCH();
+    if (int rc = launch_exclusive_scan(ix->cell_start, n_scan, tile_sums, st)) return rc;
 
-    scatter_kernel<<<grid, 256, 0, st>>>(xyz, n, ix->codes, ix->cell_start, ix->pos_of, ix->sorted);
+    scatter_kernel<<<grid, 256, 0, st>>>(xyz, n, ix->codes, ix->cell_start, ix->pos_of, ix->sorted, ix->idx_sorted);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;
 }

@@ -129,15 +129,15 @@ def gmm_handle(w, mu, sigma, device=None):
 # --------------------------------------------------------------------------------------------------
 
 def grid_cell_scale(n_points):
-    """Grid cell edge as a multiple of the largest query radius.  One cell per radius (27 candidate cells) is the
-    fastest for PCPNet-size clouds; dense clouds pay for the 2.9x overscan of that layout on every re-scan, and
-    finer cells (125 / 343 candidate cells, pruned by box distance) win: measured 12.0 -> 9.2 -> 7.3 ms per 1024
-    queries on a 10 M-point cloud at 1, 1/2 and 1/3, break-even near 400 k points (profiles/r01_configs.jsonl).
+    """Grid cell edge as a multiple of the largest query radius.  One cell per radius (27 candidate cells, flat scan)
+    is the fastest for PCPNet-size clouds.  Dense clouds get fine cells (1/8 of the radius up to 4 M points, 1/16
+    above): the library then answers with the hierarchical kernel, which accepts cells wholly inside a ball without
+    looking at their points and tests only the cells that straddle a sphere (profiles/r02_ball_query_dense.md).
     Results never depend on the grid."""
-    if n_points >= 1500000:
-        return 0.34
+    if n_points >= 4000000:
+        return 1.0 / 16.0
     if n_points >= 400000:
-        return 0.5
+        return 0.125
     return 1.0
 
 

@@ -11,14 +11,63 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_TUNED = None
+
+# constants of the fp32 forward-error model of oracle_mups_f64: per-term relative error
+# eps (C0 + C1 (ss + ss_min)), accumulation eps CSUM sqrt(m) sum|term|
+BOUND_C0, BOUND_C1, BOUND_CSUM = 8.0, 4.0, 1.0
+
+
+def _stale(so, srcs):
+    return not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs)
 
 
 def build(force=False):
     so = os.path.join(_HERE, "libmups_oracle.so")
-    src = os.path.join(_HERE, "mups_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    mk = os.path.join(_HERE, "Makefile")
+    if force or _stale(so, [os.path.join(_HERE, "mups_oracle.c"), mk]):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libmups_oracle.so"], stdout=subprocess.DEVNULL)
+    tuned = os.path.join(_HERE, "libmups_oracle_tuned.so")
+    if force or _stale(tuned, [os.path.join(_HERE, "mups_oracle_tuned.c"), mk]):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libmups_oracle_tuned.so"], stdout=subprocess.DEVNULL)
     return so
+
+
+def build_tuned_native():
+    """Rebuild the tuned CPU implementation with -march=native on the host that is about to time it (bench.py's CPU
+    legs); keeps the shipped x86-64-v3 build when the compiler is missing or fails.  Returns the -march used."""
+    global _TUNED
+    native = os.path.join(_HERE, "libmups_oracle_tuned_native.so")
+    try:
+        subprocess.check_call(["/usr/bin/gcc", "-O3", "-march=native", "-ffast-math", "-fopenmp", "-fPIC", "-shared", "-o",
+                               native, os.path.join(_HERE, "mups_oracle_tuned.c"), "-lm"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _TUNED = _load_tuned(native)
+        return "native"
+    except Exception:
+        _TUNED = None
+        return "x86-64-v3"
+
+
+def _load_tuned(path):
+    L = ctypes.CDLL(path)
+    fp = ctypes.POINTER(ctypes.c_float)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    L.oracle_mups_tuned.argtypes = [fp, ip, fp, fp, fp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
+    L.oracle_mups_tuned.restype = ctypes.c_int
+    L.oracle_tuned_set_num_threads.argtypes = [ctypes.c_int]
+    L.oracle_tuned_set_num_threads.restype = None
+    return L
+
+
+def tuned_lib():
+    global _TUNED
+    if _TUNED is None:
+        so = os.path.join(_HERE, "libmups_oracle_tuned.so")
+        if not os.path.exists(so):
+            build()
+        _TUNED = _load_tuned(so)
+    return _TUNED
 
 
 def lib():
@@ -37,6 +86,10 @@ def lib():
         L.oracle_selection_keys.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ip, ctypes.c_int64,
                                             ctypes.POINTER(ctypes.c_uint32)]
         L.oracle_selection_keys.restype = None
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.oracle_mups_f64.argtypes = [fp, ip, fp, fp, fp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp]
+        L.oracle_mups_f64.restype = ctypes.c_int
         L.oracle_num_threads.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_set_num_threads.restype = None
@@ -59,6 +112,7 @@ def num_threads():
 def set_num_threads(n):
     """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
     lib().oracle_set_num_threads(int(n))
+    tuned_lib().oracle_tuned_set_num_threads(int(n))
 
 
 def get_3dmfv(points, w, mu, sigma, n_eff=None, masked=True):
@@ -101,3 +155,45 @@ def selection_keys(seed, center, scale, nbr):
     lib().oracle_selection_keys(int(seed), int(center), int(scale), _i(nbr), len(nbr),
                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
     return out
+
+
+def mups_tuned(points, n_eff, w, mu, sigma, S):
+    """The tuned CPU implementation (mups_oracle_tuned.c): same signature and layout as mups()."""
+    points = np.ascontiguousarray(points, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    mu = np.ascontiguousarray(mu, np.float32)
+    sigma = np.ascontiguousarray(sigma, np.float32)
+    B = points.shape[0]
+    P = points.shape[1] // S
+    G = mu.shape[0]
+    res = int(round(G ** (1.0 / 3.0)))
+    ne = np.ascontiguousarray(n_eff, np.int32)
+    out = np.empty((B, res, res, res, 20 * S) if res ** 3 == G else (B, G, 20 * S), np.float32)
+    rc = tuned_lib().oracle_mups_tuned(_f(points), _i(ne), _f(w), _f(mu), _f(sigma), B, S, P, G, _f(out))
+    if rc:
+        raise MemoryError("oracle_mups_tuned")
+    return out
+
+
+def mups_f64(points, n_eff, w, mu, sigma, S, c0=BOUND_C0, c1=BOUND_C1, csum=BOUND_CSUM, masked=True):
+    """float64 evaluation of the reference formula in the MuPS layout and the per-element forward-error bound of an
+    fp32 evaluation of it (oracle_mups_f64): (truth, bound), both float64 [B,res,res,res,20*S]."""
+    points = np.ascontiguousarray(points, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    mu = np.ascontiguousarray(mu, np.float32)
+    sigma = np.ascontiguousarray(sigma, np.float32)
+    B = points.shape[0]
+    P = points.shape[1] // S
+    G = mu.shape[0]
+    res = int(round(G ** (1.0 / 3.0)))
+    ne = np.ascontiguousarray(n_eff if n_eff is not None else np.full((B, S), P), np.int32).reshape(B, S)
+    shape = (B, res, res, res, 20 * S) if res ** 3 == G else (B, G, 20 * S)
+    out = np.empty(shape, np.float64)
+    bound = np.empty(shape, np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    rc = lib().oracle_mups_f64(_f(points), _i(ne), _f(w), _f(mu), _f(sigma), B, S, P, G, 1 if masked else 0, float(c0), float(c1),
+                               float(csum),
+                               out.ctypes.data_as(dp), bound.ctypes.data_as(dp))
+    if rc:
+        raise MemoryError("oracle_mups_f64")
+    return out, bound

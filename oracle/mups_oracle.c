@@ -11,7 +11,9 @@
  * arithmetic in fp32 and is itself checked against oracle/mups_oracle.py (the
  * op-by-op numpy transliteration) in tests/test_oracle.py.
  *
- * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).
+ * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile): optimised, but no
+ * FMA contraction and no fast-math, so the arithmetic stays the literal fp32 op sequence.  oracle/mups_oracle_tuned.c
+ * is the tuned CPU implementation bench.py times beside it.
  */
 #include <math.h>
 #include <stdint.h>
@@ -177,6 +179,135 @@ int oracle_mups(const float* points, const int32_t* n_eff, const float* w, const
         }
         free(e);
         free(fv);
+    }
+    return err;
+}
+
+/* float64 evaluation of get_3dmfv_n_est (tf_util.py:655-753) in the MuPS layout + a per-element forward-error bound
+ * of an fp32 evaluation of the same formula.  For every (patch, Gaussian, channel):
+ *
+ *   raw statistic      u = reduce_n term_n                         (sum / max / min over the unmasked slots)
+ *   fp32 error model   |fl(term_n) - term_n| <= eps (c0 + c1 (ss_ng + ss_min,n)) |term_n|,  eps = 2^-24
+ *                      ss_ng  = squared standardised distance of point n to Gaussian g (the exp argument is
+ *                               -ss/2: its rounding error is relative to ss, and exp turns it into a relative
+ *                               error of the pdf); ss_min,n = the same for the Gaussian nearest to n, which
+ *                               dominates the posterior's normaliser;
+ *                      sums add the accumulation error  eps csum sqrt(m) sum_n |term_n|   (probabilistic bound,
+ *                               Higham & Mary 2019: error of an m-term sum grows like sqrt(m) eps, not m eps)
+ *   bound_u            = eps [ sum_n (c0 + c1 (ss_ng + ss_min,n) + csum sqrt(m)) |term_n| ]        for the 7 sum channels
+ *                      = eps max_n (c0 + c1 (ss_ng + ss_min,n)) |term_n|                           for max / min
+ *                        (for d_pi the w-compensation term m w / sqrt(w) enters with 3 eps)
+ *   y = u k / n_eff, by = bound_u k / n_eff + 2 eps |y|
+ *   x = sign(y) sqrt|y|:  bx = by / sqrt|y| + eps |x|  if |y| > by,  else  2.5 sqrt(by)
+ *   z = x / N, N = sqrt(max(sum_g x^2, 1e-12)):  bz = bx / N + |x| sqrt(sum_g bx^2) / N^2 + 3 eps |z|
+ *
+ * out / bound: [B, G, 20 S] doubles.  c0, c1, csum are passed in (tests state them).  masked == 0 evaluates get_3dmfv
+ * (tf_util.py:578-652) instead: nothing masked, full-sigma prefactor, 1/P. */
+int oracle_mups_f64(const float* points, const int32_t* n_eff, const float* w, const float* mu, const float* sigma,
+                    int64_t B, int S, int P, int G, int masked, double c0, double c1, double csum, double* out, double* bound) {
+    int err = 0;
+    const double eps = ldexp(1.0, -24);
+    const double pref0 = pow(2.0 * M_PI, 1.5);
+#pragma omp parallel
+    {
+        double* e = (double*)malloc(sizeof(double) * (size_t)G * 2);          /* e_g, ss_g */
+        double* u = (double*)malloc(sizeof(double) * 40 * (size_t)G);         /* u[20][G], bu[20][G] */
+        if (!e || !u) {
+#pragma omp atomic write
+            err = 1;
+        } else {
+#pragma omp for schedule(dynamic, 1) collapse(2)
+            for (int64_t b = 0; b < B; ++b)
+                for (int s = 0; s < S; ++s) {
+                    const float* pts = points + (b * S + s) * (int64_t)P * 3;
+                    const int ne = masked ? n_eff[b * S + s] : P;       /* get_3dmfv: static P, nothing masked (:618-628) */
+                    const int m = ne + 1 < P ? ne + 1 : P;
+                    const int any_masked = m < P;
+                    double* ss = e + G;
+                    double* bu = u + 20 * (size_t)G;
+                    for (int g = 0; g < G; ++g) {
+                        for (int c = 0; c < 20; ++c) { u[c * G + g] = 0.0; bu[c * G + g] = 0.0; }
+                        u[0 * G + g] = -INFINITY;
+                        for (int k = 0; k < 3; ++k) {
+                            u[(2 + k) * G + g] = -INFINITY; u[(5 + k) * G + g] = INFINITY;
+                            u[(11 + k) * G + g] = -INFINITY; u[(14 + k) * G + g] = INFINITY;
+                        }
+                    }
+                    const double acc = csum * sqrt((double)m);
+                    for (int n = 0; n < m; ++n) {
+                        double denom = 0.0, ssmin = INFINITY;
+                        for (int g = 0; g < G; ++g) {
+                            double q = 0.0;
+                            for (int k = 0; k < 3; ++k) {
+                                const double t = ((double)pts[3 * n + k] - (double)mu[3 * g + k]) / (double)sigma[3 * g + k];
+                                q += t * t;
+                            }
+                            ss[g] = q;
+                            if (q < ssmin) ssmin = q;
+                            const double s0 = (double)sigma[3 * g];
+                            const double vol = masked ? s0 * s0 * s0                      /* :687 sigma_0^D */
+                                                      : s0 * (double)sigma[3 * g + 1] * (double)sigma[3 * g + 2];   /* MultivariateNormalDiag */
+                            e[g] = (double)w[g] / (pref0 * vol) * exp(-0.5 * q);
+                            denom += e[g];
+                        }
+                        for (int g = 0; g < G; ++g) {
+                            const double Q = e[g] / denom;
+                            const double rho = c0 + c1 * (ss[g] + ssmin);
+                            const double rsw = 1.0 / sqrt((double)w[g]);
+                            const double dpi = (Q - (double)w[g]) * rsw;
+                            if (dpi > u[0 * G + g]) u[0 * G + g] = dpi;
+                            { const double bb = rho * Q * rsw + 3.0 * (double)w[g] * rsw; if (bb > bu[0 * G + g]) bu[0 * G + g] = bb; }
+                            u[1 * G + g] += dpi;
+                            bu[1 * G + g] += (rho + acc) * Q * rsw + 3.0 * (double)w[g] * rsw;
+                            for (int k = 0; k < 3; ++k) {
+                                const double t = ((double)pts[3 * n + k] - (double)mu[3 * g + k]) / (double)sigma[3 * g + k];
+                                const double dm = Q * t, ds = Q * (t * t - 1.0);
+                                const double am = fabs(dm), as = Q * (t * t + 1.0);   /* |Q t^2| + |Q|: the cancelling operands */
+                                if (dm > u[(2 + k) * G + g]) u[(2 + k) * G + g] = dm;
+                                if (dm < u[(5 + k) * G + g]) u[(5 + k) * G + g] = dm;
+                                u[(8 + k) * G + g] += dm;
+                                if (rho * am > bu[(2 + k) * G + g]) bu[(2 + k) * G + g] = rho * am;
+                                if (rho * am > bu[(5 + k) * G + g]) bu[(5 + k) * G + g] = rho * am;
+                                bu[(8 + k) * G + g] += (rho + acc) * am;
+                                if (ds > u[(11 + k) * G + g]) u[(11 + k) * G + g] = ds;
+                                if (ds < u[(14 + k) * G + g]) u[(14 + k) * G + g] = ds;
+                                u[(17 + k) * G + g] += ds;
+                                if (rho * as > bu[(11 + k) * G + g]) bu[(11 + k) * G + g] = rho * as;
+                                if (rho * as > bu[(14 + k) * G + g]) bu[(14 + k) * G + g] = rho * as;
+                                bu[(17 + k) * G + g] += (rho + acc) * as;
+                            }
+                        }
+                    }
+                    for (int c = 0; c < 20; ++c) {
+                        const int is_max = c == 0 || (c >= 2 && c < 5) || (c >= 11 && c < 14);
+                        const int is_min = (c >= 5 && c < 8) || (c >= 14 && c < 17);
+                        double sq = 0.0, sqb = 0.0;
+                        for (int g = 0; g < G; ++g) {
+                            double v = u[c * G + g], bv = eps * bu[c * G + g];
+                            if (any_masked && is_max && v < 0.0) v = 0.0;     /* masked slots: exact zeros (:698,703) */
+                            if (any_masked && is_min && v > 0.0) v = 0.0;
+                            const double k = c < 2 ? 1.0 : (c < 11 ? 1.0 / sqrt((double)w[g]) : 1.0 / sqrt(2.0 * (double)w[g]));
+                            const double y = v * k / (double)ne;
+                            const double by = bv * k / (double)ne + 2.0 * eps * fabs(y);
+                            const double x = y > 0.0 ? sqrt(y) : (y < 0.0 ? -sqrt(-y) : 0.0);
+                            const double bx = fabs(y) > by ? by / sqrt(fabs(y)) + eps * fabs(x) : 2.5 * sqrt(by);
+                            u[c * G + g] = x;
+                            bu[c * G + g] = bx;
+                            sq += x * x;
+                            sqb += bx * bx;
+                        }
+                        const double N = sqrt(sq > 1e-12 ? sq : 1e-12);
+                        for (int g = 0; g < G; ++g) {
+                            const double x = u[c * G + g], z = x / N;
+                            const int64_t o = (b * (int64_t)G + g) * 20 * S + s * 20 + c;
+                            out[o] = z;
+                            bound[o] = bu[c * G + g] / N + fabs(x) * sqrt(sqb) / (N * N) + 3.0 * eps * fabs(z);
+                        }
+                    }
+                }
+        }
+        free(e);
+        free(u);
     }
     return err;
 }

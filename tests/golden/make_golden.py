@@ -23,6 +23,12 @@ half2_reference_numpy.npz -- outputs of the reference's own numpy code run
     (``get_3dmfv_n_est(..., _posterior="pdf")``) against the reference itself; and
     ``utils/utils.py::fisher_vector_per_point`` (:214-245), whose per-point terms use the posterior
     (sklearn ``predict_proba``) and pin that stage too.  Only the n_eff mask exists in the TF code alone.
+half2_tf_emulated.npz -- outputs of the reference's own TensorFlow source text
+    (utils/tf_util.py::get_3dmfv_n_est / get_3dmfv, the MuPS loop of
+    models/experts_n_est.py::get_model), extracted with `ast` and executed with
+    `tf` bound to tests/golden/tf1_emulation.py (numpy emulation of the
+    primitive TF ops): the mask stage and the anisotropic prefactor run as the
+    reference wrote them.
 half2_oracle.npz -- inputs/outputs of the recorded fp32 transliteration of
     utils/tf_util.py:655-753 / :578-652 (TensorFlow 1.12 is not installable:
     PARITY UNPINNED), written only after the independent float64 restatement
@@ -370,6 +376,99 @@ def make_half2_reference_numpy():
     np.savez_compressed(os.path.join(HERE, "half2_reference_numpy.npz"), **out)
 
 
+def _reference_function_source(path, name):
+    """Source text of top-level function `name` in the reference file `path` (unmodified)."""
+    import ast
+    src = open(path).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            return ast.get_source_segment(src, node)
+    raise KeyError(name)
+
+
+def _reference_mups_loop_source(path):
+    """The MuPS statements of models/experts_n_est.py::get_model (:59-76): the lines from `n_rads = len(radius)` to the
+    end of the `for s in range(n_rads)` loop, as written in the reference.  (Cut out textually: the file as shipped
+    does not parse -- an unbalanced parenthesis at :103 -- so `ast` cannot be used on it.)"""
+    lines = open(path).read().split("\n")
+    top = next(i for i, ln in enumerate(lines) if ln.startswith("def get_model("))
+    first = next(i for i, ln in enumerate(lines) if i > top and ln.strip().startswith("n_rads = len(radius)"))
+    last = next(i for i, ln in enumerate(lines) if i > first and ln.strip().startswith("experts_prob = scale_manager_net("))
+    pad = len(lines[first]) - len(lines[first].lstrip())
+    return "\n".join(ln.rstrip("\r")[pad:] if ln.strip() else "" for ln in lines[first:last])
+
+
+def make_half2_tf_emulated():
+    """half2_tf_emulated.npz: the REFERENCE'S OWN TensorFlow code for half 2 -- utils/tf_util.py::get_3dmfv_n_est
+    (:655-753), ::get_3dmfv (:578-652) and the MuPS loop of models/experts_n_est.py::get_model (:59-76) -- executed
+    statement for statement in this container with `tf` bound to tests/golden/tf1_emulation.py (a numpy emulation of
+    the ~25 primitive TF ops those functions call; TensorFlow 1.12 itself cannot be installed).  This is the only
+    fixture that pins the n_eff mask stage (:691-703) and the sigma_0^3 prefactor for anisotropic sigma against the
+    reference's text rather than against a restatement of it."""
+    sys.path.insert(0, HERE)
+    import tf1_emulation as tf
+    ns = {"tf": tf, "np": np}
+    for fn in ("get_3dmfv_n_est", "get_3dmfv"):
+        exec(compile(_reference_function_source("/root/reference/utils/tf_util.py", fn), "tf_util.py::" + fn, "exec"), ns)
+    loop_src = _reference_mups_loop_source("/root/reference/models/experts_n_est.py")
+
+    class _TfUtil(object):
+        get_3dmfv_n_est = staticmethod(ns["get_3dmfv_n_est"])
+
+    rng = np.random.RandomState(77)
+    out = {}
+    cases = {
+        "g3": dict(gmm=orc.gmm_feed(*orc.get_3d_grid_gmm([3, 3, 3], 0.11)), P=24, B=10),
+        "g8": dict(gmm=orc.gmm_feed(*orc.get_3d_grid_gmm([8, 8, 8], 0.0156)), P=40, B=9),
+    }
+    G = 11
+    w = rng.uniform(0.5, 1.5, G)
+    cases["gen"] = dict(gmm=((w / w.sum()).astype(np.float32), rng.uniform(-0.8, 0.8, (G, 3)).astype(np.float32),
+                             rng.uniform(0.2, 0.6, (G, 3)).astype(np.float32)), P=17, B=8)
+    for name, c in cases.items():
+        w, mu, sg = c["gmm"]
+        P, B = c["P"], c["B"]
+        edge = [1, 2, 3, P // 2, P - 2, P - 1, P]
+        ne = np.array([edge[b % len(edge)] for b in range(B)], np.int32)
+        pts = np.zeros((B, P, 3), np.float32)
+        for b in range(B):
+            x = rng.normal(size=(ne[b], 3)) * rng.uniform(0.15, 0.6)
+            x /= np.maximum(1.0, np.linalg.norm(x, axis=1, keepdims=True))
+            x[0] = 0
+            pts[b, :ne[b]] = x
+        tp, tw, tmu, tsg = tf.Tensor(pts), tf.Tensor(w), tf.Tensor(mu), tf.Tensor(sg)
+        flat = ns["get_3dmfv_n_est"](tp, tw, tmu, tsg, flatten=True, n_original_points=tf.Tensor(ne)).a
+        cube = ns["get_3dmfv_n_est"](tp, tw, tmu, tsg, flatten=False, n_original_points=tf.Tensor(ne)).a
+        plain = ns["get_3dmfv"](tp, tw, tmu, tsg, flatten=False).a
+        assert flat.dtype == np.float32 and flat.shape == (B, 20 * len(w)) and cube.shape == (B, 20, len(w))
+        assert np.array_equal(flat.reshape(B, 20, len(w)), cube)
+        out.update({name + "_points": pts, name + "_n_eff": ne, name + "_w": w, name + "_mu": mu, name + "_sigma": sg,
+                    name + "_fv_n_est": cube, name + "_fv_plain": plain})
+        # the transliteration of oracle/ must agree with the reference's text run on the emulated ops
+        mine = orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False, n_original_points=ne)
+        err = np.abs(mine - cube)
+        assert np.all(err <= 1e-6 + 1e-5 * np.abs(cube)), (name, float(err.max()))
+        mine = orc.get_3dmfv(pts, w, mu, sg, flatten=False)
+        err = np.abs(mine - plain)
+        assert np.all(err <= 1e-6 + 1e-5 * np.abs(plain)), (name + " plain", float(err.max()))
+        print("tf-emulated %s: get_3dmfv_n_est %s, get_3dmfv %s" % (name, cube.shape, plain.shape))
+    # MuPS assembly (experts_n_est.py:59-76): two scales of the g3 case
+    w, mu, sg = cases["g3"]["gmm"]
+    P, B = cases["g3"]["P"], cases["g3"]["B"]
+    pts2 = np.concatenate([out["g3_points"], out["g3_points"][::-1]], axis=1)
+    ne2 = np.stack([out["g3_n_eff"], out["g3_n_eff"][::-1]], axis=1)
+    env = {"tf": tf, "np": np, "tf_util": _TfUtil, "points": tf.Tensor(pts2), "w": tf.Tensor(w), "mu": tf.Tensor(mu),
+           "sigma": tf.Tensor(sg), "radius": [0.05, 0.1], "original_n_points": tf.Tensor(ne2), "range": range, "len": len,
+           "int": int}
+    exec(compile(loop_src, "experts_n_est.py::get_model[MuPS]", "exec"), env)
+    mups = env["MuPS"].a
+    assert mups.shape == (B, 3, 3, 3, 40)
+    out.update({"mups_points": pts2, "mups_n_eff": ne2, "mups_out": mups})
+    assert np.allclose(mups, orc.mups_assemble(pts2, w, mu, sg, ne2, 2), rtol=1e-5, atol=1e-6)
+    np.savez_compressed(os.path.join(HERE, "half2_tf_emulated.npz"), **out)
+    print("tf-emulated MuPS %s" % (mups.shape,))
+
+
 def make_rotation_reference():
     """utils/eulerangles.py::euler2mat and the augmentation of train_n_est_w_experts.py:262-272 run on the
     unmodified reference module (a py2 builtin, ``reduce``, is supplied from functools)."""
@@ -404,3 +503,4 @@ if __name__ == "__main__":
     make_half2_reference_numpy()
     make_rotation_reference()
     make_half2()
+    make_half2_tf_emulated()

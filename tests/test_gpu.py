@@ -19,41 +19,49 @@ TOL_ABS, TOL_REL = 1e-6, 1e-5          # BASELINE.json north_star: 3DmFV within 
 SEED = 3627473                          # the reference's constant (test_n_est_w_experts.py:113)
 
 
-def assert_features_close(got, ref, what="", truth=None):
-    """|a-b| <= 1e-6 + 1e-5|b| element-wise against the fp32 oracle `ref`.
+def check_features(got, patches, n_eff, w, mu, sg, S, what="", layout="mups", masked=True, ref32=None):
+    """The feature gate, with NO tolerated exceptions: every element of `got` must lie within
+    |a-b| <= 1e-6 + 1e-5|b| of the FLOAT64 evaluation of the reference formula (oracle_mups_f64), or -- where the
+    formula is ill-conditioned: a sum channel that cancels almost completely in front of the signed square root --
+    within the forward-error bound of an fp32 evaluation that oracle_mups_f64 derives from the same data
+    (eps (c0 + c1 ss) |term| per pair, eps csum sqrt(m) sum|term| for the accumulation, propagated through /n_eff, the
+    square root and the channel norm).  If an fp32 oracle result `ref32` is given, `got` must also
+    agree with it within the band or twice the bound (both are fp32 evaluations).  Rows with n_eff == 0 are last-batch
+    padding: NaN in the reference, skipped.
 
-    The reference's formula is ill-conditioned where a sum channel is a near-complete fp32
-    cancellation (the signed square root has unbounded slope at 0), so ANY two fp32 evaluations
-    -- the two CPU oracles included, tests/test_oracle.py::test_c_port_on_realistic_patches --
-    disagree beyond the band on a ~1e-6..1e-4 fraction of elements (DESIGN.md 'Tolerance').
-    Elements outside the band must therefore be few and either be within the band of the float64
-    evaluation `truth` of the same formula (callable returning it), or be explained by fp32 noise
-    of the statistic before the square root (x = sign(u) sqrt|u|, sum_g |u_g| = 1: |du| <= 2e-7)."""
-    got = np.asarray(got, np.float64)
-    ref = np.asarray(ref, np.float64)
-    assert got.shape == ref.shape, (got.shape, ref.shape)
-    ok = np.isfinite(ref)
-    assert np.array_equal(np.isfinite(got), ok), what + ": non-finite pattern differs"
-    err = np.where(ok, np.abs(got - np.where(ok, ref, 0)), 0)
-    bad = err > TOL_ABS + TOL_REL * np.abs(np.where(ok, ref, 0))
-    frac = float(bad.mean()) if bad.size else 0.0
-    if bad.any() and truth is not None:
-        t = np.asarray(truth() if callable(truth) else truth, np.float64).reshape(got.shape)
-        bad &= np.abs(got - t) > TOL_ABS + TOL_REL * np.abs(t)
-    assert int(bad.sum()) <= max(4, 1e-4 * bad.size), \
-        "%s: %d of %d elements outside 1e-5 rel / 1e-6 abs (max err %.3g)" % (what, int(bad.sum()), bad.size, err.max())
-    du = np.abs(got * np.abs(got) - ref * np.abs(ref))
-    assert not bad.any() or du[bad].max() <= 2e-7, "%s: excursion not explained by cancellation (du %.3g)" % (what, du[bad].max())
-    assert err.max() < 5e-4, "%s: max err %.3g" % (what, err.max())
-    return frac
+    layout: 'mups' [B, ..., 20 S]; 'channel' [B, S, 20, G]; 'fv' [B, 20, G] or [B, 20 G] (one scale).
+    Returns (elements outside the band, max err / bound among them)."""
+    patches = np.asarray(patches, np.float32)
+    B, G = len(patches), len(w)
+    truth, bound = c_oracle.mups_f64(patches, n_eff, w, mu, sg, S, masked=masked)
+    truth, bound = truth.reshape(B, G, S, 20), bound.reshape(B, G, S, 20)
 
-
-def f64_mups(pts, ne, w, mu, sg, S):
-    """float64 evaluation of the reference formula in the MuPS layout [B, G, S*20] (flattened)."""
-    B = len(pts)
-    P = pts.shape[1] // S
-    out = np.stack([orc.get_3dmfv_n_est_f64(pts[:, s * P:(s + 1) * P], w, mu, sg, ne[:, s]) for s in range(S)], 0)
-    return out.transpose(1, 3, 0, 2).reshape(B, -1)                     # [S,B,20,G] -> [B,G,S,20]
+    def to_bgsc(x):
+        x = np.asarray(x, np.float64)
+        if layout == "mups":
+            return x.reshape(B, G, S, 20)
+        if layout == "channel":
+            return x.reshape(B, S, 20, G).transpose(0, 3, 1, 2)
+        assert layout == "fv" and S == 1
+        return x.reshape(B, 20, G).transpose(0, 2, 1)[:, :, None, :]
+    got = to_bgsc(got)
+    real = np.ones((B, S), bool) if (n_eff is None or not masked) else (np.asarray(n_eff).reshape(B, S) > 0)
+    rows = np.broadcast_to(real[:, None, :, None], got.shape)
+    assert np.all(np.isfinite(got[rows])), what + ": non-finite feature"
+    err = np.where(rows, np.abs(got - np.where(rows, truth, 0)), 0)
+    band = TOL_ABS + TOL_REL * np.abs(np.where(rows, truth, 0))
+    lim = np.maximum(band, np.where(rows, bound, 0))
+    bad = err > lim
+    assert not bad.any(), "%s: %d of %d elements outside 1e-5 rel / 1e-6 abs of float64 AND outside the fp32 error bound " \
+        "(max err %.3g, worst err/bound %.3g)" % (what, int(bad.sum()), bad.size, err.max(), float((err / np.maximum(lim, 1e-300)).max()))
+    outside = err > band
+    worst = float((err[outside] / bound[outside]).max()) if outside.any() else 0.0
+    if ref32 is not None:
+        r = to_bgsc(ref32)
+        e2 = np.where(rows, np.abs(got - np.where(rows, r, 0)), 0)
+        assert np.all(e2 <= np.maximum(TOL_ABS + TOL_REL * np.abs(np.where(rows, r, 0)), 2 * np.where(rows, bound, 0))), \
+            "%s: disagrees with the fp32 oracle beyond band and bound (max %.3g)" % (what, e2.max())
+    return int(outside.sum()), worst
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -79,6 +87,15 @@ def grid_gmm(res, var):
     return orc.gmm_feed(*orc.get_3d_grid_gmm([res] * 3, var))
 
 
+@pytest.fixture(params=["auto", "hier"])
+def query_kernel(request):
+    """Half-1 tests run twice: automatic kernel choice (flat cell scan on coarse grids) and the hierarchical kernel
+    forced (mups_set_option "query_kernel" = 2) -- the results may not differ in a single bit."""
+    _lib.set_option("query_kernel", 2 if request.param == "hier" else 0)
+    yield request.param
+    _lib.set_option("query_kernel", 0)
+
+
 # =====================================================================================================
 # half 1: index + ball query + subsample + normalise
 # =====================================================================================================
@@ -92,7 +109,7 @@ def run_half1(pts, q, radius, P, seed=SEED, cell_frac=None, indices=True):
 
 
 @pytest.mark.parametrize("case", ["A", "B"])
-def test_half1_against_reference_fixture(half1, case):
+def test_half1_against_reference_fixture(half1, case, query_kernel):
     """Against outputs of the unmodified reference (tests/golden/make_golden.py)."""
     g = {k[len(case) + 1:]: half1[k] for k in half1.files if k.startswith(case + "_")}
     pts, q, P = g["pts"], g["query_idx"], int(g["P"])
@@ -131,7 +148,7 @@ def test_half1_against_reference_fixture(half1, case):
     (30000, 1024, [0.05, 0.1], "pcpnet", 1),
     (40000, 128, [0.015, 0.35, 0.2], "pcpnet", 77),                     # > 4096 neighbours: the hit list overflows, re-scan path
 ])
-def test_half1_against_oracle(n, P, radius, kind, seed):
+def test_half1_against_oracle(n, P, radius, kind, seed, query_kernel):
     pts = orc.synthetic_cloud(n, cloud_id=4, kind=kind, noise=0.002)
     q = np.random.RandomState(1).choice(n, 96, replace=False)
     _, _, (patches, n_eff, total, nbr) = run_half1(pts, q, radius, P, seed=seed)
@@ -144,24 +161,65 @@ def test_half1_against_oracle(n, P, radius, kind, seed):
 
 
 def test_half1_grid_cell_scale():
-    """Dense clouds get finer grid cells (mb.mups.grid_cell_scale): same neighbours, same patches."""
-    assert mb.mups.grid_cell_scale(100000) == 1.0 and mb.mups.grid_cell_scale(450000) == 0.5
-    assert mb.mups.grid_cell_scale(10000000) == 0.34
+    """Dense clouds get fine grid cells (mb.mups.grid_cell_scale) and with them the hierarchical kernel; the former
+    1/2 and 1/3 cells with the flat kernel forced are the re-scan regime of round 1: same neighbours, same patches."""
+    assert mb.mups.grid_cell_scale(100000) == 1.0 and mb.mups.grid_cell_scale(450000) == 0.125
+    assert mb.mups.grid_cell_scale(10000000) == 0.0625
     radius, P = [0.01, 0.03, 0.07], 256
-    for n, scale in ((450000, None), (60000, 0.34), (60000, 0.5)):
-        pts = orc.synthetic_cloud(n, cloud_id=11, kind="scan" if n > 100000 else "pcpnet", noise=0.001)
-        q = np.random.RandomState(5).choice(n, 24, replace=False)
-        index = mb.PointIndex(pts, cell_frac=max(radius), cell_scale=scale)
-        patches, n_eff, total, nbr = index.ball_query(torch.from_numpy(q).cuda(), index.absolute_radii(radius), P,
-                                                      seed=SEED, return_indices=True)
-        o_patches, o_neff, o_total, o_nbr = orc.gather_patches(pts, q, radius, P, seed=SEED, return_indices=True)
-        assert np.array_equal(total.cpu().numpy(), o_total), (n, scale)
-        assert np.array_equal(nbr.cpu().numpy(), o_nbr), (n, scale)
-        assert np.array_equal(patches.cpu().numpy().view(np.uint32), o_patches.view(np.uint32)), (n, scale)
-        assert np.array_equal(n_eff.cpu().numpy(), o_neff)
+    try:
+        for n, scale, kernel in ((450000, None, 0), (450000, 0.5, 1), (60000, 0.34, 1), (60000, 0.5, 1), (60000, 0.125, 0),
+                                 (60000, 0.0625, 0), (60000, 0.03, 2)):
+            _lib.set_option("query_kernel", kernel)
+            pts = orc.synthetic_cloud(n, cloud_id=11, kind="scan" if n > 100000 else "pcpnet", noise=0.001)
+            q = np.random.RandomState(5).choice(n, 24, replace=False)
+            index = mb.PointIndex(pts, cell_frac=max(radius), cell_scale=scale)
+            patches, n_eff, total, nbr = index.ball_query(torch.from_numpy(q).cuda(), index.absolute_radii(radius), P,
+                                                          seed=SEED, return_indices=True)
+            o_patches, o_neff, o_total, o_nbr = orc.gather_patches(pts, q, radius, P, seed=SEED, return_indices=True)
+            assert np.array_equal(total.cpu().numpy(), o_total), (n, scale)
+            assert np.array_equal(nbr.cpu().numpy(), o_nbr), (n, scale)
+            assert np.array_equal(patches.cpu().numpy().view(np.uint32), o_patches.view(np.uint32)), (n, scale)
+            assert np.array_equal(n_eff.cpu().numpy(), o_neff)
+    finally:
+        _lib.set_option("query_kernel", 0)
 
 
-def test_half1_edge_cases():
+@pytest.mark.parametrize("n,kind,noise,P,radius,scale,order", [
+    (300000, "pcpnet", 0.0, 512, [0.01, 0.03, 0.05, 0.07], 0.125, 0),
+    (300000, "scan", 0.0005, 256, [0.07, 0.02, 0.05], 0.0625, 2),            # radii not ascending, 8 Morton bits, CTAs reordered
+    (200000, "pcpnet", 0.01, 1024, [0.05, 0.1], 0.125, 0),                    # thick noisy shell: many occupied cells
+    (100000, "pcpnet", 0.0, 64, [0.01, 0.02, 0.04, 0.06, 0.08, 0.1, 0.12, 0.2], 0.125, 2),   # 8 scales
+    (150000, "scan", 0.0, 512, [0.3], 0.0625, 0),                             # one huge ball: bulk nodes far above the leaves
+    (50000, "pcpnet", 0.0, 2048, [0.05, 0.2], 0.125, 0),                      # lists too large for the hierarchical kernel: flat
+])
+def test_half1_hierarchical_kernel(n, kind, noise, P, radius, scale, order):
+    """The hierarchical kernel (octree descent over the Morton-ordered cells, whole-cell acceptance, one-pass key
+    threshold) against cKDTree + the shared seeded selection: counts, selected indices and patches bit-exact; also
+    with the hand-over to the flat kernel forced for about half of the balls (hier_margin = 0)."""
+    pts = orc.synthetic_cloud(n, cloud_id=14, kind=kind, noise=noise)
+    q = np.random.RandomState(9).choice(n, 128, replace=False)
+    ref = orc.gather_patches(pts, q, radius, P, seed=SEED, return_indices=True)
+    try:
+        _lib.set_option("query_kernel", 2)
+        _lib.set_option("query_order", order)
+        for margin in (-1, 0):
+            _lib.set_option("hier_margin", margin)
+            index = mb.PointIndex(pts, cell_frac=max(radius), cell_scale=scale)
+            out = index.ball_query(q, index.absolute_radii(radius), P, seed=SEED, return_indices=True)
+            patches, n_eff, total, nbr = [t.cpu().numpy() for t in out]
+            assert np.array_equal(total, ref[2]), "neighbour counts differ from cKDTree (margin %d)" % margin
+            assert np.array_equal(n_eff, ref[1])
+            assert np.array_equal(nbr, ref[3]), "selected indices differ (margin %d)" % margin
+            assert np.array_equal(patches.view(np.uint32), ref[0].view(np.uint32)), "patches not bit-exact"
+    finally:
+        _lib.set_option("query_kernel", 0)
+        _lib.set_option("query_order", 0)
+        _lib.set_option("hier_margin", -1)
+    if P <= 1024:
+        assert (ref[2] > P).any()
+
+
+def test_half1_edge_cases(query_kernel):
     rng = np.random.RandomState(2)
     # single point, two identical points, tiny cloud
     for pts in (np.zeros((1, 3), np.float32) + 0.5,
@@ -206,7 +264,7 @@ def test_half1_edge_cases():
         index.ball_query(q, [0.1], 4096)
 
 
-def test_half1_cell_size_independent_and_refinement_levels():
+def test_half1_cell_size_independent_and_refinement_levels(query_kernel):
     """Results do not depend on the grid resolution, on the query order, or on the size of the
     radix threshold group (boundary_cap lowered so the refinement levels run)."""
     pts = orc.synthetic_cloud(40000, cloud_id=7, noise=0.001)
@@ -262,9 +320,9 @@ def test_half2_against_golden_fixture(half2, case, fastpath):
     gmm = mb.gmm_handle(w, mu, sg)
     assert gmm.separable == (case != "gen")
     got = mb.stats_3dmfv(pts, ne, gmm, 1, masked=True, layout="channel", fastpath=fastpath).cpu().numpy()[:, 0]
-    assert_features_close(got, half2[case + "_fv_n_est"], case + " n_est")
+    check_features(got, pts, ne, w, mu, sg, 1, case + " n_est", layout="fv", ref32=half2[case + "_fv_n_est"])
     got = mb.stats_3dmfv(pts, None, gmm, 1, masked=False, layout="channel", fastpath=fastpath).cpu().numpy()[:, 0]
-    assert_features_close(got, half2[case + "_fv_plain"], case + " plain")
+    check_features(got, pts, None, w, mu, sg, 1, case + " plain", layout="fv", masked=False, ref32=half2[case + "_fv_plain"])
 
 
 @pytest.mark.parametrize("fastpath", [True, False])
@@ -279,9 +337,32 @@ def test_half2_against_reference_run_fixture(golden_dir, case, fastpath):
     gmm = mb.gmm_handle(w, mu, sg)
     got = mb.stats_3dmfv(pts, np.full((B, 1), P, np.int32), gmm, 1, masked=True, layout="channel",
                          fastpath=fastpath).cpu().numpy()[:, 0]
-    assert_features_close(got, ref[case + "_fv"], case + " vs reference run")
+    check_features(got, pts, np.full((B, 1), P, np.int32), w, mu, sg, 1, case + " vs reference run", layout="fv",
+                   ref32=ref[case + "_fv"])
     plain = mb.stats_3dmfv(pts, None, gmm, 1, masked=False, layout="channel", fastpath=fastpath).cpu().numpy()[:, 0]
-    assert_features_close(plain, ref[case + "_fv"], case + " get_3dmfv vs reference run")     # isotropic sigma: same pdf
+    check_features(plain, pts, None, w, mu, sg, 1, case + " get_3dmfv vs reference run", layout="fv", masked=False,
+                   ref32=ref[case + "_fv"])                                                    # isotropic sigma: same pdf
+
+
+@pytest.mark.parametrize("fastpath", [True, False])
+@pytest.mark.parametrize("case", ["g3", "g8", "gen"])
+def test_half2_against_reference_text_on_emulated_tf(golden_dir, case, fastpath):
+    """Both CUDA kernels against tests/golden/half2_tf_emulated.npz: outputs of the reference's OWN TensorFlow source
+    text (utils/tf_util.py::get_3dmfv_n_est / get_3dmfv) executed with the primitive ops emulated in numpy -- the one
+    fixture that pins the n_eff mask stage and the anisotropic prefactor (n_eff in {1, 2, 3, P/2, P-2, P-1, P})."""
+    ref = np.load(os.path.join(golden_dir, "half2_tf_emulated.npz"))
+    pts, ne, w, mu, sg = (ref["%s_%s" % (case, k)] for k in ("points", "n_eff", "w", "mu", "sigma"))
+    gmm = mb.gmm_handle(w, mu, sg)
+    got = mb.stats_3dmfv(pts, ne, gmm, 1, masked=True, layout="channel", fastpath=fastpath).cpu().numpy()[:, 0]
+    check_features(got, pts, ne, w, mu, sg, 1, case + " n_est vs reference text", layout="fv", ref32=ref[case + "_fv_n_est"])
+    got = mb.stats_3dmfv(pts, None, gmm, 1, masked=False, layout="channel", fastpath=fastpath).cpu().numpy()[:, 0]
+    check_features(got, pts, None, w, mu, sg, 1, case + " plain vs reference text", layout="fv", masked=False,
+                   ref32=ref[case + "_fv_plain"])
+    if case == "g3":       # MuPS assembly (experts_n_est.py:59-76, also run from the reference's text)
+        p2, n2 = ref["mups_points"], ref["mups_n_eff"]
+        got = mb.stats_3dmfv(p2, n2, gmm, 2, fastpath=fastpath).cpu().numpy()
+        assert got.shape == ref["mups_out"].shape
+        check_features(got, p2, n2, w, mu, sg, 2, "MuPS vs reference text", ref32=ref["mups_out"])
 
 
 def test_half2_reference_signatures(half2):
@@ -293,9 +374,11 @@ def test_half2_reference_signatures(half2):
     cube = mb.tf_util.get_3dmfv_n_est(torch.from_numpy(pts).cuda(), w, mu, sg, flatten=False,
                                       n_original_points=torch.from_numpy(ne.astype(np.uint16).astype(np.int32)))
     assert cube.shape == (B, 20, G) and torch.equal(cube.reshape(B, -1), flat)
-    assert_features_close(flat.cpu().numpy(), orc.get_3dmfv_n_est(pts, w, mu, sg, True, ne), "flatten=True")
+    check_features(flat.cpu().numpy(), pts, ne, w, mu, sg, 1, "flatten=True", layout="fv",
+                   ref32=orc.get_3dmfv_n_est(pts, w, mu, sg, True, ne))
     plain = mb.tf_util.get_3dmfv(pts, w, mu, sg, flatten=False)
-    assert_features_close(plain.cpu().numpy(), orc.get_3dmfv(pts, w, mu, sg, flatten=False), "get_3dmfv")
+    check_features(plain.cpu().numpy(), pts, None, w, mu, sg, 1, "get_3dmfv", layout="fv", masked=False,
+                   ref32=orc.get_3dmfv(pts, w, mu, sg, flatten=False))
     with pytest.raises(ValueError):
         mb.tf_util.get_3dmfv_n_est(pts, w, mu, sg)                   # the reference fails on None too
     with pytest.raises(ValueError):
@@ -327,8 +410,7 @@ def test_half2_mups_layout_against_oracle(res, P, S, var, fastpath):
         mb.stats_3dmfv(pts, ne, mb.gmm_handle(w, mu, sg), S, fastpath=False)
     assert tuple(got.shape) == (B, res, res, res, 20 * S)
     ref = c_oracle.mups(pts, ne, w, mu, sg, S) if res >= 8 else orc.mups_assemble(pts, w, mu, sg, ne, S)
-    assert_features_close(got.cpu().numpy(), ref, "mups res=%d P=%d S=%d" % (res, P, S),
-                          truth=lambda: f64_mups(pts, ne, w, mu, sg, S))
+    check_features(got.cpu().numpy(), pts, ne, w, mu, sg, S, "mups res=%d P=%d S=%d" % (res, P, S), ref32=ref)
     # channel layout is the same numbers transposed
     ch = mb.stats_3dmfv(pts, ne, mb.gmm_handle(w, mu, sg), S, layout="channel", fastpath=fastpath).cpu().numpy()
     assert np.array_equal(ch.transpose(0, 3, 1, 2).reshape(B, res, res, res, 20 * S), got.cpu().numpy())
@@ -359,8 +441,8 @@ def test_half2_kernel_variants(variant, res, var):
     finally:
         _lib.set_option("stats_variant", 0)
     ref = c_oracle.mups(pts, ne, w, mu, sg, S)
-    assert_features_close(got, ref, "variant %d res %d" % (variant, res), truth=lambda: f64_mups(pts, ne, w, mu, sg, S))
-    assert_features_close(base, ref, "default res %d" % res, truth=lambda: f64_mups(pts, ne, w, mu, sg, S))
+    check_features(got, pts, ne, w, mu, sg, S, "variant %d res %d" % (variant, res), ref32=ref)
+    check_features(base, pts, ne, w, mu, sg, S, "default res %d" % res, ref32=ref)
 
 
 def test_half2_general_gmm_and_padding_rows():
@@ -373,7 +455,7 @@ def test_half2_general_gmm_and_padding_rows():
     pts = rng.uniform(-0.8, 0.8, (B, S * P, 3)).astype(np.float32)      # garbage beyond n_eff on purpose:
     got = mb.stats_3dmfv(pts, ne, mb.gmm_handle(w, mu, sg), S).cpu().numpy()   # slot n_eff takes part, the rest not
     ref = c_oracle.mups(pts, ne, w, mu, sg, S).reshape(got.shape)
-    assert_features_close(got, ref, "general gmm")
+    check_features(got, pts, ne, w, mu, sg, S, "general gmm", ref32=ref)
     p2 = pts.copy()
     for b in range(B):
         for s in range(S):
@@ -402,7 +484,9 @@ def test_end_to_end_against_oracle():
     o_patches, o_neff, o_total = orc.gather_patches(pts, q, radius, P, seed=SEED)
     assert np.array_equal(total.cpu().numpy(), o_total) and np.array_equal(n_eff.cpu().numpy(), o_neff)
     assert np.array_equal(patches.cpu().numpy().view(np.uint32), o_patches.view(np.uint32))
-    assert_features_close(feats.cpu().numpy(), c_oracle.mups(o_patches, o_neff, w, mu, sg, 4), "end to end")
+    n_out, worst = check_features(feats.cpu().numpy(), o_patches, o_neff, w, mu, sg, 4, "end to end",
+                                  ref32=c_oracle.mups(o_patches, o_neff, w, mu, sg, 4))
+    print("end to end: %d of %d elements outside the 1e-5/1e-6 band of float64 (worst err/bound %.3g)" % (n_out, feats.numel(), worst))
 
 
 def test_dataset_drop_in(tmp_path, half1):
@@ -532,12 +616,14 @@ def test_full_size_properties():
     assert torch.equal(mb.mups_features(index, gmm, q[perm], radii_abs, P, seed=SEED), feats[torch.from_numpy(perm).cuda()])
     # general (non-separable) kernel agrees with the fast path
     slow = mb.mups_features(index, gmm, q[:1024], radii_abs, P, seed=SEED, fastpath=False)
-    assert_features_close(slow.cpu().numpy(), feats[:1024].cpu().numpy(), "general vs separable")
+    check_features(slow[:256].cpu().numpy(), pa.reshape(len(q), 4 * P, 3)[:256], ne[:256], w, mu, sg, 4, "general kernel at full size",
+                   ref32=feats[:256].cpu().numpy())
     # oracle spot check at full cloud size
     sub = np.arange(0, len(q), 64)
     o_patches, o_neff, o_total = orc.gather_patches(pts, q[sub], radius, P, seed=SEED)
     assert np.array_equal(tot[sub], o_total) and np.array_equal(pa[sub].reshape(len(sub), 4 * P, 3), o_patches)
-    assert_features_close(feats.cpu().numpy()[sub], c_oracle.mups(o_patches, o_neff, w, mu, sg, 4), "full size")
+    check_features(feats.cpu().numpy()[sub], o_patches, o_neff, w, mu, sg, 4, "full size",
+                   ref32=c_oracle.mups(o_patches, o_neff, w, mu, sg, 4))
 
 
 def test_smoke_entry_point():

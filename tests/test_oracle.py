@@ -262,3 +262,64 @@ def test_c_port_on_realistic_patches():
     c = c_oracle.mups(patches, n_eff, w, mu, sg, 4)
     assert frac_outside(c, a) < 2e-5
     assert np.abs(c - a).max() < 1e-4
+
+
+# ---- half 2 against the reference's own TensorFlow text run on emulated ops ------------------------------------------
+
+@pytest.fixture(scope="module")
+def half2_tf(golden_dir):
+    return np.load(os.path.join(golden_dir, "half2_tf_emulated.npz"))
+
+
+@pytest.mark.parametrize("case", ["g3", "g8", "gen"])
+def test_half2_pinned_by_reference_text_on_emulated_tf(half2_tf, case):
+    """tests/golden/half2_tf_emulated.npz holds outputs of utils/tf_util.py::get_3dmfv_n_est / get_3dmfv EXECUTED FROM
+    THE REFERENCE'S SOURCE TEXT with `tf` bound to a numpy emulation of the primitive ops (make_golden.py): it pins the
+    n_eff mask (:691-703) and the sigma_0^3 prefactor (anisotropic 'gen' case) -- the one stage no reference numpy code
+    covers -- for the transliteration, its C port and the float64 restatement, with n_eff in {1, 2, 3, P/2, P-2, P-1, P}."""
+    pts, ne, w, mu, sg = (half2_tf["%s_%s" % (case, k)] for k in ("points", "n_eff", "w", "mu", "sigma"))
+    ref = half2_tf[case + "_fv_n_est"]
+    assert frac_outside(orc.get_3dmfv_n_est(pts, w, mu, sg, flatten=False, n_original_points=ne), ref) == 0.0
+    assert frac_outside(c_oracle.get_3dmfv(pts, w, mu, sg, ne, masked=True), ref) == 0.0
+    assert frac_outside(orc.get_3dmfv_n_est_f64(pts, w, mu, sg, ne), ref) == 0.0
+    plain = half2_tf[case + "_fv_plain"]
+    assert frac_outside(orc.get_3dmfv(pts, w, mu, sg, flatten=False), plain) == 0.0
+    assert frac_outside(c_oracle.get_3dmfv(pts, w, mu, sg, None, masked=False), plain) == 0.0
+    # the mask really is `slot > n_eff`: a perturbation of slot n_eff changes the reference's output, slot n_eff + 1 does not
+    B, P, _ = pts.shape
+    b = int(np.argmax((ne >= 2) & (ne < P - 2)))
+    moved = pts.copy()
+    moved[b, ne[b] + 1] = 0.3
+    assert np.array_equal(orc.get_3dmfv_n_est(moved, w, mu, sg, False, ne)[b], orc.get_3dmfv_n_est(pts, w, mu, sg, False, ne)[b])
+    moved[b, ne[b]] = 0.3
+    assert not np.array_equal(orc.get_3dmfv_n_est(moved, w, mu, sg, False, ne)[b], orc.get_3dmfv_n_est(pts, w, mu, sg, False, ne)[b])
+
+
+def test_mups_assembly_pinned_by_reference_text(half2_tf):
+    """The MuPS loop of models/experts_n_est.py::get_model (:59-76) executed from the reference's text (py2 integer
+    division, reshape [B,-1,res,res,res], transpose [0,2,3,4,1], concat) against mups_assemble and the C port."""
+    pts, ne, ref = half2_tf["mups_points"], half2_tf["mups_n_eff"], half2_tf["mups_out"]
+    w, mu, sg = half2_tf["g3_w"], half2_tf["g3_mu"], half2_tf["g3_sigma"]
+    assert frac_outside(orc.mups_assemble(pts, w, mu, sg, ne, 2), ref) == 0.0
+    assert frac_outside(c_oracle.mups(pts, ne, w, mu, sg, 2), ref) == 0.0
+    truth, bound = c_oracle.mups_f64(pts, ne, w, mu, sg, 2)
+    assert frac_outside(truth, ref) == 0.0 and np.all(bound >= 0) and np.all(np.isfinite(bound))
+
+
+def test_forward_error_bound_covers_the_fp32_oracles():
+    """every element of an fp32 evaluation lies within 1e-5 rel / 1e-6 abs of the float64 value OR
+    within the forward-error bound oracle_mups_f64 derives from the data (no tolerated exceptions).  Checked here for the
+    two CPU fp32 evaluations (literal port, tuned port) on realistic patches; the GPU tests apply the same criterion."""
+    w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([8] * 3, 0.0156))
+    pts = orc.synthetic_cloud(30000, cloud_id=5, noise=0.001)
+    q = np.random.RandomState(2).choice(30000, 48, replace=False)
+    pa, ne, _ = orc.gather_patches(pts, q, [0.01, 0.03, 0.05, 0.07], 512)
+    truth, bound = c_oracle.mups_f64(pa, ne, w, mu, sg, 4)
+    band = TOL_ABS + TOL_REL * np.abs(truth)
+    for name, got in (("literal", c_oracle.mups(pa, ne, w, mu, sg, 4)), ("tuned", c_oracle.mups_tuned(pa, ne, w, mu, sg, 4))):
+        err = np.abs(got - truth)
+        assert np.all(err <= np.maximum(band, bound)), name
+        outside = err > band
+        assert outside.mean() < 1e-4                                   # the bound is only needed for a handful
+    # the bound is not a blanket allowance: for the typical element it is below the contract's band
+    assert np.median(bound / band) < 1.0
