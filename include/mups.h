@@ -114,7 +114,9 @@ int mups_ball_query(const mups_index* index, const int64_t* query_idx_dev, int64
 
 /* ---- GMM ----------------------------------------------------------------------------------- */
 /* w [G], mu [G,3], sigma [G,3] (std-dev) float32 on the HOST.  Detects the separable lattice
- * (tensor-product means, one sigma per axis, uniform w) produced by get_3d_grid_gmm. */
+ * (tensor-product means, one sigma per axis, uniform w) produced by get_3d_grid_gmm.
+ * w <= 0, sigma <= 0 or non-finite parameters are rejected with MUPS_ERR_INVALID (the reference would propagate
+ * NaN / Inf through sqrt(w) and 1/sigma; get_3d_grid_gmm cannot produce them). */
 int mups_gmm_create(mups_gmm** out, const float* w_host, const float* mu_host, const float* sigma_host, int G);
 int mups_gmm_size(const mups_gmm* gmm);
 int mups_gmm_is_separable(const mups_gmm* gmm);
@@ -122,7 +124,11 @@ void mups_gmm_destroy(mups_gmm* gmm);
 
 /* ---- half 2: 3DmFV statistics (K5) ---------------------------------------------------------- */
 /* patches_dev [B, S*P, 3] float32; n_eff_dev [B,S] int32 (required with MUPS_FLAG_MASKED, else
- * ignored and may be NULL); out_dev: B*S*20*G float32 in the layout selected by `flags`. */
+ * ignored and may be NULL); out_dev: B*S*20*G float32 in the layout selected by `flags`.
+ * Rows with n_eff == 0 are last-batch padding (test_n_est_w_experts.py:134-140): the reference divides by zero there
+ * and so does this kernel (NaN / Inf rows, to be dropped by the caller as the reference's loop does).  A NEGATIVE n_eff
+ * cannot come out of the reference's dataset (effective_points_num is min(P, len) >= 1); it is treated as 0, where the
+ * reference would mask nothing and divide by the negative count. */
 int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_eff_dev,
                int64_t B, int S, int P, uint32_t flags, float* out_dev, mups_stream stream);
 

@@ -31,8 +31,9 @@ def estimate_normals(indir, dataset_name, outdir, model, gmm, patch_radius, poin
     handle = _m.gmm_handle(gmm.weights_, gmm.means_, np.sqrt(gmm.covariances_))
     model_device = next(model.parameters()).device
     model.eval()
+    cudnn_benchmark = torch.backends.cudnn.benchmark
     if model_device.type == "cuda":
-        torch.backends.cudnn.benchmark = True      # the 8^3 conv3d stack is 2-3x faster with cuDNN's tuned algorithms
+        torch.backends.cudnn.benchmark = True      # the 8^3 conv3d stack is 2-3x faster with cuDNN's tuned algorithms (restored below)
     n_rads = len(patch_radius)
     normals, experts, probs = [], [], []
     for data in loader:
@@ -42,6 +43,7 @@ def estimate_normals(indir, dataset_name, outdir, model, gmm, patch_radius, poin
         normals.append(normal.float().cpu().numpy())
         experts.append(expert.cpu().numpy())
         probs.append(prob.float().cpu().numpy())
+    torch.backends.cudnn.benchmark = cudnn_benchmark
     normals, experts, probs = np.concatenate(normals), np.concatenate(experts), np.concatenate(probs)
     out, offset = {}, 0
     if write and not os.path.exists(outdir):

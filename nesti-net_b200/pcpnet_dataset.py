@@ -4,8 +4,8 @@
 (utils/pcpnet_dataset.py:182-183), item layout (:419) and the attributes its callers read
 (``shape_names``, ``shape_patch_count``, ``patch_radius_absolute``).  The per-item kd-tree query,
 subsample, centring and normalisation (:303-343) run in the ball-query kernel of
-libmups_b200.so; ``get_batch`` answers a whole batch of patch indices in one launch and is
-what ``provider.get_data_loader`` iterates.
+libmups_b200.so; ``get_batch`` answers a whole batch of patch indices with one launch per distinct
+shape of the batch and is what ``provider.get_data_loader`` iterates.
 
 Only the options every reference script uses are on the hot path (``use_pca=False``,
 ``center='point'``, ``point_tuple=1``, ``point_count_std=0``); the others raise.
@@ -34,10 +34,12 @@ class Shape(object):
 
 
 def _load_table(path, dtype):
-    """Text table (``.xyz`` / ``.normals`` / ``.curv`` / ``.pidx``) -> array; a ``.npy`` sibling
-    written by the reference (pcpnet_dataset.py:251) is used when present."""
-    if os.path.exists(path + ".npy"):
-        return np.load(path + ".npy").astype(dtype)
+    """Text table (``.xyz`` / ``.normals`` / ``.curv`` / ``.pidx``) -> array.  A ``.npy`` sibling written by the
+    reference (pcpnet_dataset.py:251) is used only while it is at least as new as the text file: the reference
+    regenerates it from the text in every constructor (:250-251), so an edited text file must win over a stale ``.npy``."""
+    npy = path + ".npy"
+    if os.path.exists(npy) and (not os.path.exists(path) or os.path.getmtime(npy) >= os.path.getmtime(path)):
+        return np.load(npy).astype(dtype)
     return np.loadtxt(path).astype(dtype)
 
 
@@ -230,48 +232,52 @@ class PointcloudPatchDataset(torch.utils.data.Dataset):
         index = PointIndex(pts, cell_frac=max(self.patch_radius))
         return Shape(pts, index, normals=normals, curv=curv, pidx=pidx, noise_level=self.noise_levels[shape_ind])
 
-    # ---- batched access: one ball-query launch per shape run --------------------------------------
+    # ---- batched access: one ball-query launch per distinct shape of the batch ------------------------------
     def get_batch(self, indices):
         """[points [B,S*P,3] f32 (CUDA), *targets, trans [B,3,3], n_eff [B,S] (float64 like the
         collated reference item, CUDA)] -- the list a DataLoader batch of the reference holds
-        (provider.py:319-429)."""
+        (provider.py:319-429).  The batch is grouped by shape (stable, so the order inside a shape is the caller's):
+        ONE ball-query launch per distinct shape whatever the sampling order -- the reference's training order
+        ('random', train_n_est_w_experts.py:232) interleaves the shapes patch by patch -- and each shape is fetched from
+        the cache once per batch."""
         indices = np.asarray(indices, dtype=np.int64).reshape(-1)
         B, S, P = len(indices), len(self.patch_radius), self.points_per_patch
-        shape_inds = np.searchsorted(self._offsets, indices, side='right') - 1
         if B and (indices.min() < 0 or indices.max() >= self._offsets[-1]):
             raise IndexError("patch index out of range")
+        shape_inds = np.searchsorted(self._offsets, indices, side='right') - 1
         dev = torch.device('cuda', torch.cuda.current_device())
         points = torch.empty((B, S * P, 3), dtype=torch.float32, device=dev)
         n_eff = torch.empty((B, S), dtype=torch.int32, device=dev)
-        centers = np.empty(B, dtype=np.int64)
-        # consecutive runs of the same shape (samplers keep a shape's patches adjacent)
-        start = 0
-        while start < B:
-            end = start
-            while end < B and shape_inds[end] == shape_inds[start]:
-                end += 1
-            shape_ind = int(shape_inds[start])
-            shape = self.shape_cache.get(shape_ind)
-            local = indices[start:end] - self._offsets[shape_ind]
-            c = local if shape.pidx is None else shape.pidx[local]
-            centers[start:end] = c
-            p, ne, _ = shape.index.ball_query(c, self.patch_radius_absolute[shape_ind], P, seed=self.selection_seed())
-            points[start:end] = p
-            n_eff[start:end] = ne
-            start = end
-        feats = []
+        feats = {}
         for pfeat in self.patch_features:
-            rows = []
-            for b in range(B):
-                shape = self.shape_cache.get(int(shape_inds[b]))
+            width = {'normal': 3, 'max_curvature': 1, 'min_curvature': 1}.get(pfeat)
+            feats[pfeat] = np.empty((B,) if width is None else (B, width), dtype=np.float64 if width is None else np.float32)
+        order = np.argsort(shape_inds, kind='stable')
+        cuts = np.flatnonzero(np.diff(shape_inds[order])) + 1
+        for rows in np.split(order, cuts):
+            if not len(rows):
+                continue
+            shape_ind = int(shape_inds[rows[0]])
+            shape = self.shape_cache.get(shape_ind)
+            local = indices[rows] - self._offsets[shape_ind]
+            c = local if shape.pidx is None else shape.pidx[local]
+            radii = self.patch_radius_absolute[shape_ind]
+            p, ne, _ = shape.index.ball_query(c, radii, P, seed=self.selection_seed())
+            if len(rows) == B:                              # one shape: the launch wrote the batch in order
+                points, n_eff = p, ne
+            else:
+                at = torch.as_tensor(rows, device=dev)
+                points.index_copy_(0, at, p)
+                n_eff.index_copy_(0, at, ne)
+            for pfeat in self.patch_features:
                 if pfeat == 'normal':
-                    rows.append(shape.normals[centers[b], :])
+                    feats[pfeat][rows] = shape.normals[c, :]
                 elif pfeat == 'max_curvature':
-                    rows.append(shape.curv[centers[b], 0:1] * self.patch_radius_absolute[int(shape_inds[b])][0])
+                    feats[pfeat][rows] = shape.curv[c, 0:1] * radii[0]
                 elif pfeat == 'min_curvature':
-                    rows.append(shape.curv[centers[b], 1:2] * self.patch_radius_absolute[int(shape_inds[b])][0])
+                    feats[pfeat][rows] = shape.curv[c, 1:2] * radii[0]
                 elif pfeat == 'noise':
-                    rows.append(np.asarray(shape.noise_level, dtype=np.float64))
-            feats.append(torch.as_tensor(np.stack(rows)) if rows else torch.empty(0))
+                    feats[pfeat][rows] = shape.noise_level
+        targets = [torch.as_tensor(feats[pfeat]) for pfeat in self.patch_features]
         trans = torch.eye(3, dtype=torch.float32).repeat(B, 1, 1)
-        return [points] + feats + [trans, n_eff.to(torch.float64)]
+        return [points] + targets + [trans, n_eff.to(torch.float64)]

@@ -74,7 +74,7 @@ class MuPSPipeline(object):
 
     def features_to_host(self, pts_host, query_idx_host=None, consume=None):
         """Streams the MuPS rows of every query of one cloud to the host.  `consume(lo, hi, rows)`
-        is called with a pinned numpy view [hi-lo, 20*S*G] per chunk (valid only during the call).
+        is called with a pinned numpy view [hi-lo, 20*S*G] per chunk, in ascending order of `lo` (valid only during the call).
         Returns the number of query points processed."""
         compute = torch.cuda.current_stream(self.device)
         index, radii, q = self._stage_in(pts_host, query_idx_host)
@@ -102,6 +102,7 @@ class MuPSPipeline(object):
                 self._copied[k].record(self._copy_stream)
             pending[k] = (lo, hi)
             self.d2h_bytes += (hi - lo) * self.row_floats * 4
-        drain(0)
-        drain(1)
+        last = (len(range(0, B, self.chunk)) - 1) & 1      # buffer of the newest chunk: the other one holds the older chunk
+        drain(last ^ 1)
+        drain(last)
         return B

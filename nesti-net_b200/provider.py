@@ -1,8 +1,8 @@
 """Drop-in for ``provider.get_data_loader`` of the reference (utils/provider.py:319-429): same
 arguments and return value ``(dataloader, dataset)``; iterating the loader yields
 ``[points [B,S*P,3], *targets, trans [B,3,3], n_eff [B,S]]`` exactly like a collated reference
-batch, but a batch is produced by one ball-query launch on the GPU instead of B kd-tree queries
-on one Python thread (``workers`` is accepted and ignored: there is no host loop to parallelise).
+batch, but a batch is produced by one ball-query launch per distinct shape in it instead of B kd-tree
+queries on one Python thread (``workers`` is accepted and ignored: there is no host loop to parallelise).
 """
 import math
 

@@ -90,6 +90,10 @@ def lib():
         L.oracle_mups_f64.argtypes = [fp, ip, fp, fp, fp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp]
         L.oracle_mups_f64.restype = ctypes.c_int
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        L.oracle_half1_gather.argtypes = [fp, i64p, ctypes.c_int64, ctypes.c_float, i64p, i64p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_uint64, fp, ip]
+        L.oracle_half1_gather.restype = ctypes.c_int
         L.oracle_num_threads.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_set_num_threads.restype = None
@@ -197,3 +201,21 @@ def mups_f64(points, n_eff, w, mu, sigma, S, c0=BOUND_C0, c1=BOUND_C1, csum=BOUN
     if rc:
         raise MemoryError("oracle_mups_f64")
     return out, bound
+
+
+def half1_gather(pts, query_idx, rad, lists, P, S, scale, seed, patches, n_eff):
+    """Selection + gather + centre + normalise of one radius for a batch (oracle_half1_gather, OpenMP): `lists` are the
+    neighbour lists cKDTree.query_ball_point returned for the batch; fills patches[:, scale*P:(scale+1)*P] and n_eff[:, scale]."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    q = np.ascontiguousarray(query_idx, np.int64)
+    lens = np.fromiter((len(l) for l in lists), np.int64, len(lists))
+    off = np.zeros(len(lists) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = np.fromiter((j for l in lists for j in l), np.int64, int(off[-1])) if off[-1] < 200000 else \
+        np.concatenate([np.asarray(l, np.int64) for l in lists])
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    rc = lib().oracle_half1_gather(_f(pts), q.ctypes.data_as(i64p), len(q), ctypes.c_float(np.float32(rad)),
+                                   flat.ctypes.data_as(i64p), off.ctypes.data_as(i64p), int(P), int(S), int(scale),
+                                   int(seed) & (2 ** 64 - 1), _f(patches), _i(n_eff))
+    if rc:
+        raise MemoryError("oracle_half1_gather")

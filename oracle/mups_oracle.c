@@ -118,7 +118,10 @@ static void fv_one(const float* pts, int P, int n_eff, const float* w, const flo
     }
     const float npts = masked ? (float)n_eff : 1.0f;   /* :722-730; get_3dmfv folds 1/P into the scale factors */
     for (int c = 0; c < 20; ++c) {
-        float sq = 0.f;
+        /* sum of squares over the Gaussians: tf.nn.l2_normalize reduces with Eigen's tree / packet reduction (numpy:
+         * pairwise), whose error stays ~1e-7; a sequential fp32 loop over thousands of nearly equal terms drifts
+         * systematically (2.5e-5 at G = 4096), an artefact a port must not add -- accumulated in double, rounded once */
+        double sq = 0.0;
         for (int g = 0; g < G; ++g) {
             float v = st[c * G + g];
             if (c >= 2 && c < 11) v = (masked ? 1.0f / sqrtf(w[g]) : 1.0f / ((float)P * sqrtf(w[g]))) * v;            /* :715 / :623 */
@@ -126,9 +129,10 @@ static void fv_one(const float* pts, int P, int n_eff, const float* w, const flo
             v = v / npts;                      /* :728-730 */
             v = signed_sqrt(v);                /* :733-736 */
             st[c * G + g] = v;
-            sq += v * v;
+            sq += (double)(v * v);
         }
-        const float inv = 1.0f / sqrtf(sq > 1e-12f ? sq : 1e-12f);   /* tf.nn.l2_normalize, :739-741 */
+        const float sqf = (float)sq;
+        const float inv = 1.0f / sqrtf(sqf > 1e-12f ? sqf : 1e-12f);   /* tf.nn.l2_normalize, :739-741 */
         for (int g = 0; g < G; ++g) st[c * G + g] *= inv;
     }
 }
@@ -196,7 +200,8 @@ int oracle_mups(const float* points, const int32_t* n_eff, const float* w, const
  *                               Higham & Mary 2019: error of an m-term sum grows like sqrt(m) eps, not m eps)
  *   bound_u            = eps [ sum_n (c0 + c1 (ss_ng + ss_min,n) + csum sqrt(m)) |term_n| ]        for the 7 sum channels
  *                      = eps max_n (c0 + c1 (ss_ng + ss_min,n)) |term_n|                           for max / min
- *                        (for d_pi the w-compensation term m w / sqrt(w) enters with 3 eps)
+ *                        (for d_pi the -w / sqrt(w) term of every slot enters with 3 eps, and in the sum channel with the
+ *                        accumulation factor as well: tf.reduce_sum adds m terms of size sqrt(w))
  *   y = u k / n_eff, by = bound_u k / n_eff + 2 eps |y|
  *   x = sign(y) sqrt|y|:  bx = by / sqrt|y| + eps |x|  if |y| > by,  else  2.5 sqrt(by)
  *   z = x / N, N = sqrt(max(sum_g x^2, 1e-12)):  bz = bx / N + |x| sqrt(sum_g bx^2) / N^2 + 3 eps |z|
@@ -258,7 +263,7 @@ int oracle_mups_f64(const float* points, const int32_t* n_eff, const float* w, c
                             if (dpi > u[0 * G + g]) u[0 * G + g] = dpi;
                             { const double bb = rho * Q * rsw + 3.0 * (double)w[g] * rsw; if (bb > bu[0 * G + g]) bu[0 * G + g] = bb; }
                             u[1 * G + g] += dpi;
-                            bu[1 * G + g] += (rho + acc) * Q * rsw + 3.0 * (double)w[g] * rsw;
+                            bu[1 * G + g] += (rho + acc) * Q * rsw + (3.0 + acc) * (double)w[g] * rsw;   /* the -w/sqrt(w) terms accumulate too */
                             for (int k = 0; k < 3; ++k) {
                                 const double t = ((double)pts[3 * n + k] - (double)mu[3 * g + k]) / (double)sigma[3 * g + k];
                                 const double dm = Q * t, ds = Q * (t * t - 1.0);
@@ -333,4 +338,102 @@ void oracle_selection_keys(uint64_t seed, uint32_t center, uint32_t scale, const
     }
     const uint32_t a = c0, b = c1 | 1u;
     for (int64_t i = 0; i < n; ++i) out[i] = fmix32(((uint32_t)nbr[i] ^ a) * b);
+}
+
+/* ---- half 1 after the kd-tree query: shared seeded selection + gather + centre + normalise (pcpnet_dataset.py:310-343)
+ * for one radius, OpenMP over the queries.  nbr_flat / nbr_off: the neighbour lists of cKDTree.query_ball_point in CSR
+ * form (any order).  Same results as oracle/mups_oracle.py::gather_patches (checked in tests/test_oracle.py). */
+/* rearranges v so that v[0..k) are the k smallest (quickselect, median-of-three) */
+static void select_smallest(uint64_t* v, int64_t n, int64_t k) {
+    int64_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        uint64_t a = v[lo], b = v[mid], c = v[hi];
+        const uint64_t pivot = a < b ? (b < c ? b : (a < c ? c : a)) : (a < c ? a : (b < c ? c : b));
+        int64_t i = lo, j = hi;
+        while (i <= j) {
+            while (v[i] < pivot) ++i;
+            while (v[j] > pivot) --j;
+            if (i <= j) { const uint64_t t = v[i]; v[i] = v[j]; v[j] = t; ++i; --j; }
+        }
+        if (k - 1 <= j) hi = j;
+        else if (k - 1 >= i) lo = i;
+        else return;
+    }
+}
+static int cmp_i64(const void* a, const void* b) {
+    const int64_t x = *(const int64_t*)a, y = *(const int64_t*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+int oracle_half1_gather(const float* pts, const int64_t* query_idx, int64_t B, float rad_f32, const int64_t* nbr_flat,
+                        const int64_t* nbr_off, int P, int S, int scale, uint64_t seed, float* patches /* [B,S*P,3] */,
+                        int32_t* n_eff /* [B,S] */) {
+    int err = 0;
+#pragma omp parallel
+    {
+        uint64_t* keyed = NULL;
+        int64_t* sel = (int64_t*)malloc(sizeof(int64_t) * (size_t)P);
+        size_t cap = 0;
+        if (!sel) {
+#pragma omp atomic write
+            err = 1;
+        }
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t b = 0; b < B; ++b) {
+            if (err) continue;
+            const int64_t* nb = nbr_flat + nbr_off[b];
+            const int64_t n = nbr_off[b + 1] - nbr_off[b];
+            const int64_t c = query_idx[b];
+            const int64_t take = n < P ? n : P;
+            n_eff[b * S + scale] = (int32_t)take;
+            float* out = patches + ((size_t)b * S + scale) * (size_t)P * 3;
+            const int64_t* chosen = nb;
+            if ((size_t)n > cap) {
+                free(keyed);
+                cap = (size_t)n * 2;
+                keyed = (uint64_t*)malloc(sizeof(uint64_t) * cap);
+                if (!keyed) {
+#pragma omp atomic write
+                    err = 1;
+                    cap = 0;
+                    continue;
+                }
+            }
+            if (n > P) {
+                /* Philox4x32-10(counter = (centre, scale, 0, 0), key = seed) -> salt (a, b | 1); key(j) = fmix32((j ^ a) * b) */
+                uint32_t c0 = (uint32_t)c, c1 = (uint32_t)scale, c2 = 0, c3 = 0;
+                uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+                for (int r = 0; r < 10; ++r) {
+                    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+                    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+                    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+                    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+                    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+                }
+                const uint32_t sa = c0, sb = c1 | 1u;
+                for (int64_t i = 0; i < n; ++i)
+                    keyed[i] = ((uint64_t)fmix32(((uint32_t)nb[i] ^ sa) * sb) << 32) | (uint32_t)nb[i];
+                select_smallest(keyed, n, P);                                /* the P smallest (key, index) pairs */
+                for (int64_t i = 0; i < P; ++i) sel[i] = (int64_t)(keyed[i] & 0xFFFFFFFFull);
+                qsort(sel, (size_t)P, sizeof(int64_t), cmp_i64);
+                chosen = sel;
+            } else {
+                int64_t* tmp = (int64_t*)keyed;
+                memcpy(tmp, nb, sizeof(int64_t) * (size_t)n);
+                qsort(tmp, (size_t)n, sizeof(int64_t), cmp_i64);
+                chosen = tmp;
+            }
+            const float cx = pts[3 * c], cy = pts[3 * c + 1], cz = pts[3 * c + 2];
+            for (int64_t i = 0; i < take; ++i) {
+                const int64_t j = chosen[i];
+                out[3 * i] = (pts[3 * j] - cx) / rad_f32;
+                out[3 * i + 1] = (pts[3 * j + 1] - cy) / rad_f32;
+                out[3 * i + 2] = (pts[3 * j + 2] - cz) / rad_f32;
+            }
+        }
+        free(keyed);
+        free(sel);
+    }
+    return err;
 }

@@ -146,7 +146,7 @@ static void fv_one_tuned(const float* pts, int P, int n_eff, const gmm_soa* gm, 
     }
     for (int c = 0; c < 20; ++c) {
         float* restrict v = st + c * G;
-        float sq = 0.f;
+        double sq = 0.0;                     /* tree-accurate like Eigen / numpy reductions (see mups_oracle.c) */
         for (int g = 0; g < G; ++g) {
             float t = v[g];
             if (c >= 2) {
@@ -158,9 +158,9 @@ static void fv_one_tuned(const float* pts, int P, int n_eff, const gmm_soa* gm, 
             t *= inv_n;
             t = t > 0.f ? sqrtf(t) : (t < 0.f ? -sqrtf(-t) : 0.f);
             v[g] = t;
-            sq += t * t;
+            sq += (double)(t * t);
         }
-        const float nrm = 1.0f / sqrtf(sq > 1e-12f ? sq : 1e-12f);
+        const float nrm = 1.0f / sqrtf((float)sq > 1e-12f ? (float)sq : 1e-12f);
         for (int g = 0; g < G; ++g) v[g] *= nrm;
     }
 }

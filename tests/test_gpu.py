@@ -66,7 +66,8 @@ def check_features(got, patches, n_eff, w, mu, sg, S, what="", layout="mups", ma
 
 @pytest.fixture(scope="module", autouse=True)
 def _cuda():
-    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("-m gpu tests need a CUDA device (B200); there is no CPU fallback to test instead")
     torch.cuda.set_device(0)
     _lib.load()
     yield
@@ -574,6 +575,19 @@ def test_dataset_interface_against_reference_run(tmp_path, golden_dir):
     batch = ds.get_batch([0, 41, 89])                     # one call across both shapes
     assert np.array_equal(batch[1].numpy(), ref["item_normal"][[0, 5, 7]])
     assert np.array_equal(batch[-1].cpu().numpy(), ref["item_n_eff"][[0, 5, 7]])
+    # the training order ('random') interleaves the shapes patch by patch: still ONE ball-query launch per distinct shape,
+    # rows delivered in the caller's order
+    n = len(ds)
+    mixed = [0, n - 1, 1, n - 2, 2, n - 3, 3]
+    singles = [ds.get_batch([i]) for i in mixed]
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    inter = ds.get_batch(mixed)
+    assert _lib.launch_count() - l0 == 2, "expected one ball-query launch per distinct shape"
+    for k, one in enumerate(singles):
+        assert torch.equal(inter[0][k], one[0][0]) and torch.equal(inter[-1][k], one[-1][0])
+        for a, b in zip(inter[1:-2], one[1:-2]):
+            assert torch.equal(a[k], b[0])
 
 
 def test_full_size_properties():
@@ -624,6 +638,103 @@ def test_full_size_properties():
     assert np.array_equal(tot[sub], o_total) and np.array_equal(pa[sub].reshape(len(sub), 4 * P, 3), o_patches)
     check_features(feats.cpu().numpy()[sub], o_patches, o_neff, w, mu, sg, 4, "full size",
                    ref32=c_oracle.mups(o_patches, o_neff, w, mu, sg, 4))
+
+
+# =====================================================================================================
+# BASELINE configs[3] / configs[4]: the dense clouds at their full sizes
+# =====================================================================================================
+
+def _dense_half1_check(pts, kd, q, radius, P, what, **index_kw):
+    """Half 1 of `q` on the dense cloud against cKDTree + the shared seeded selection: everything bit-exact."""
+    index = mb.PointIndex(pts, cell_frac=max(radius), **index_kw)
+    out = index.ball_query(q, index.absolute_radii(radius), P, seed=SEED, return_indices=True)
+    patches, n_eff, total, nbr = [t.cpu().numpy() for t in out]
+    o_patches, o_neff, o_total, o_nbr = orc.gather_patches(pts, q, radius, P, seed=SEED, kdtree=kd, return_indices=True)
+    assert np.array_equal(total, o_total), what + ": neighbour counts differ from cKDTree"
+    assert np.array_equal(n_eff, o_neff) and np.array_equal(nbr, o_nbr), what + ": selected indices differ"
+    assert np.array_equal(patches.view(np.uint32), o_patches.view(np.uint32)), what + ": patches not bit-exact"
+    return patches, n_eff, total
+
+
+def test_config_c4_dense_scan_cloud_full_size():
+    """BASELINE configs[3]: 2 M-point scan-shape cloud (density spread > 20x), 4 scales, P = 512, 8^3 grid.  256 queries
+    against the oracle through the hierarchical kernel the library picks for this size (fine grid, 1/8-radius cells),
+    the flat kernel on round 1's grids (1/2 and 1/3-radius cells: hit list overflows, every pass re-scans) on 48 of
+    them; features of all 256 through the gate of check_features."""
+    n, P, radius = 2000000, 512, [0.01, 0.03, 0.05, 0.07]
+    pts = orc.synthetic_cloud(n, cloud_id=1, kind="scan")
+    kd = orc.build_kdtree(pts)
+    q = np.random.RandomState(21).choice(n, 256, replace=False)
+    assert mb.mups.grid_cell_scale(n) == 0.125
+    patches, n_eff, total = _dense_half1_check(pts, kd, q, radius, P, "hierarchical, automatic grid")
+    assert total.max() > 100000 and total[:, 0].min() < total[:, 0].max() / 20        # dense balls, non-uniform density
+    try:
+        _lib.set_option("query_kernel", 1)
+        for scale in (0.5, 0.34):
+            _dense_half1_check(pts, kd, q[:48], radius, P, "flat kernel, cell scale %g" % scale, cell_scale=scale)
+    finally:
+        _lib.set_option("query_kernel", 0)
+    w, mu, sg = grid_gmm(8, 0.0156)
+    feats = mb.stats_3dmfv(patches, n_eff, mb.gmm_handle(w, mu, sg), 4)
+    n_out, worst = check_features(feats.cpu().numpy(), patches, n_eff, w, mu, sg, 4, "configs[3] features",
+                                  ref32=c_oracle.mups(patches, n_eff, w, mu, sg, 4))
+    print("configs[3]: 256 queries, max ball %d neighbours; %d of %d feature elements outside the 1e-5/1e-6 band of float64 "
+          "(worst err/bound %.3g)" % (int(total.max()), n_out, feats.numel(), worst))
+    # work-balanced contiguous sharding of the sweep-ordered query list (SURVEY.md 8e)
+    order = np.argsort(pts[q, 2], kind="stable")
+    work = total[order].sum(1).astype(np.float64)
+    b = mb.dist.shard_bounds(len(q), 4, work)
+    loads = np.array([work[b[r]:b[r + 1]].sum() for r in range(4)])
+    even = mb.dist.shard_bounds(len(q), 4)
+    loads_even = np.array([work[even[r]:even[r + 1]].sum() for r in range(4)])
+    assert loads.max() / loads.mean() < loads_even.max() / loads_even.mean() and loads.max() / loads.mean() < 1.15
+
+
+@pytest.fixture(scope="module")
+def cloud_10m():
+    n = 10000000
+    pts = orc.synthetic_cloud(n, cloud_id=2)
+    return pts, orc.build_kdtree(pts), np.random.RandomState(22).choice(n, 256, replace=False)
+
+
+def test_config_c5_10m_points_half1(cloud_10m):
+    """BASELINE configs[4]: 10 M points, 4 scales.  256 queries at P = 512 and 64 each at P = 256 / 1024 through the
+    hierarchical kernel on the automatic grid (1/16-radius cells, 8 Morton bits); the flat kernel (round 1's 1/3-radius
+    cells) on 32 queries including the largest ball, where the 9-bit radix threshold group exceeds boundary_cap = 512
+    and the refinement levels run at their natural size."""
+    pts, kd, q = cloud_10m
+    radius = [0.01, 0.03, 0.05, 0.07]
+    assert mb.mups.grid_cell_scale(len(pts)) == 0.0625
+    _, _, total = _dense_half1_check(pts, kd, q, radius, 512, "P=512")
+    assert total.max() > 250000 and (total[:, 1:] > 100 * 512 // 2).all()
+    _dense_half1_check(pts, kd, q[:64], radius, 256, "P=256")
+    _dense_half1_check(pts, kd, q[64:128], radius, 1024, "P=1024")
+    big = np.concatenate([[int(np.argmax(total[:, 3]))], np.arange(31)])
+    try:
+        _lib.set_option("query_kernel", 1)
+        _dense_half1_check(pts, kd, q[big], radius, 512, "flat kernel, cell scale 0.34", cell_scale=0.34)
+    finally:
+        _lib.set_option("query_kernel", 0)
+
+
+@pytest.mark.parametrize("res,P,nq", [(8, 512, 256), (8, 256, 64), (8, 1024, 64), (16, 512, 64)])
+def test_config_c5_10m_points_features(cloud_10m, res, P, nq):
+    """configs[4] sweep: grid 8^3 / 16^3, P = 256 / 512 / 1024 on the 10 M-point cloud; every patch is full
+    (n_eff = P at all four scales).  Both halves on the GPU, features through the gate of check_features."""
+    pts, kd, q = cloud_10m
+    radius = [0.01, 0.03, 0.05, 0.07]
+    w, mu, sg = grid_gmm(res, 0.0156 if res == 8 else (1.0 / res) ** 2)
+    index = mb.PointIndex(pts, cell_frac=max(radius))
+    feats, patches, n_eff, total = mb.mups_features(index, mb.gmm_handle(w, mu, sg), q[:nq], index.absolute_radii(radius), P,
+                                                    seed=SEED, return_patches=True)
+    o_patches, o_neff, o_total = orc.gather_patches(pts, q[:nq], radius, P, seed=SEED, kdtree=kd)
+    assert np.array_equal(total.cpu().numpy(), o_total) and np.array_equal(n_eff.cpu().numpy(), o_neff)
+    assert np.array_equal(patches.cpu().numpy().view(np.uint32), o_patches.view(np.uint32))
+    assert (o_neff == P).all()
+    n_out, worst = check_features(feats.cpu().numpy(), o_patches, o_neff, w, mu, sg, 4, "configs[4] %d^3 P=%d" % (res, P),
+                                  ref32=c_oracle.mups(o_patches, o_neff, w, mu, sg, 4))
+    print("configs[4] %d^3 P=%d: %d queries, %d of %d elements outside the band (worst err/bound %.3g)"
+          % (res, P, nq, n_out, feats.numel(), worst))
 
 
 def test_smoke_entry_point():

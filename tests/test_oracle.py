@@ -323,3 +323,24 @@ def test_forward_error_bound_covers_the_fp32_oracles():
         assert outside.mean() < 1e-4                                   # the bound is only needed for a handful
     # the bound is not a blanket allowance: for the typical element it is below the contract's band
     assert np.median(bound / band) < 1.0
+
+
+def test_tuned_cpu_path_matches_the_oracle():
+    """The CPU legs of bench.py: the C/OpenMP half 1 (selection + gather + normalise after cKDTree) is bit-identical to
+    gather_patches, the tuned half 2 agrees with the literal port to 1e-5 -- they time the same computation."""
+    pts = orc.synthetic_cloud(20000, cloud_id=6)
+    tree = orc.build_kdtree(pts)
+    q = np.random.RandomState(4).choice(20000, 40, replace=False).astype(np.int64)
+    radius, P = [0.02, 0.05, 0.09], 96
+    ref_p, ref_ne, ref_tot = orc.gather_patches(pts, q, radius, P, seed=11, kdtree=tree)
+    assert (ref_tot > P).any() and (ref_tot <= P).any()
+    patches = np.zeros_like(ref_p)
+    n_eff = np.zeros_like(ref_ne)
+    for s, rad in enumerate(orc.absolute_radii(pts, radius)):
+        lists = tree.query_ball_point(pts[q], rad)
+        c_oracle.half1_gather(pts, q, rad, lists, P, len(radius), s, 11, patches, n_eff)
+    assert np.array_equal(n_eff, ref_ne) and np.array_equal(patches.view(np.uint32), ref_p.view(np.uint32))
+    w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([8] * 3, 0.0156))
+    a = c_oracle.mups(ref_p, ref_ne, w, mu, sg, 3)
+    b = c_oracle.mups_tuned(ref_p, ref_ne, w, mu, sg, 3)
+    assert np.abs(a - b).max() < 2e-5
