@@ -132,10 +132,27 @@ void mups_gmm_destroy(mups_gmm* gmm);
 int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_eff_dev,
                int64_t B, int S, int P, uint32_t flags, float* out_dev, mups_stream stream);
 
+/* ---- K6: selection hand-off, patches never in HBM ------------------------------------------------ */
+/* mups_ball_query without the patch tensor: nbr_pos[b][s][t] = position of the t-th selected neighbour (ascending point
+ * index) in the index's Morton-ordered point array, -1 beyond n_eff -- 4 bytes per slot instead of 12.  Opaque to the
+ * caller; only mups_3dmfv_selected with the SAME index, query list and radii can consume it. */
+int mups_ball_query_select(const mups_index* index, const int64_t* query_idx_dev, int64_t B,
+                           const double* r_abs_host, int S, int P, uint64_t seed,
+                           int32_t* nbr_pos_dev, int32_t* nbr_total_dev, int32_t* n_eff_dev, mups_stream stream);
+/* get_3dmfv_n_est + MuPS assembly of the patches a selection describes: the statistics kernel gathers the selected
+ * points from the index while it stages a patch and centres / normalises them itself ((p - c) / float32(r) in IEEE
+ * fp32: K4 folded into K5).  Bit-identical to mups_3dmfv on the patch tensor mups_ball_query would have written.
+ * MUPS_FLAG_MASKED is implied. */
+int mups_3dmfv_selected(const mups_gmm* gmm, const mups_index* index, const int64_t* query_idx_dev, int64_t B,
+                        const double* r_abs_host, int S, int P, const int32_t* nbr_pos_dev, const int32_t* n_eff_dev,
+                        uint32_t flags, float* out_dev, mups_stream stream);
+
 /* ---- both halves ---------------------------------------------------------------------------- */
 /* mups_ball_query followed by mups_3dmfv(MUPS_FLAG_MASKED) for the same B centres.
  * patches_dev / n_eff_dev are caller-provided scratch of the sizes above (kept so that the
- * caller can also read the patches); nbr_total_dev may be NULL. */
+ * caller can also read the patches); nbr_total_dev may be NULL.
+ * patches_dev == NULL selects the K6 path: mups_ball_query_select + mups_3dmfv_selected through stream-ordered library
+ * scratch (4 B*S*P bytes) -- same features bit for bit, a third of the intermediate HBM traffic, no patch tensor. */
 int mups_features(const mups_index* index, const mups_gmm* gmm, const int64_t* query_idx_dev, int64_t B,
                   const double* r_abs_host, int S, int P, uint64_t seed, uint32_t flags,
                   float* patches_dev, int32_t* n_eff_dev, int32_t* nbr_total_dev, float* out_dev,

@@ -30,7 +30,7 @@ EXPORTS = (
     "mups_index_create", "mups_index_bbox", "mups_index_size", "mups_index_destroy",
     "mups_ball_query",
     "mups_gmm_create", "mups_gmm_size", "mups_gmm_is_separable", "mups_gmm_destroy",
-    "mups_3dmfv", "mups_features",
+    "mups_3dmfv", "mups_features", "mups_ball_query_select", "mups_3dmfv_selected",
 )
 
 _lib = None
@@ -77,6 +77,10 @@ def load():
     L.mups_3dmfv.restype = i32
     L.mups_features.argtypes = [vp, vp, vp, i64, dp, i32, i32, u64, u32, vp, vp, vp, vp, vp]
     L.mups_features.restype = i32
+    L.mups_ball_query_select.argtypes = [vp, vp, i64, dp, i32, i32, u64, vp, vp, vp, vp]
+    L.mups_ball_query_select.restype = i32
+    L.mups_3dmfv_selected.argtypes = [vp, vp, vp, i64, dp, i32, i32, vp, vp, u32, vp, vp]
+    L.mups_3dmfv_selected.restype = i32
     if L.mups_abi_version() != 1:
         raise RuntimeError("libmups_b200.so ABI version %d, expected 1" % L.mups_abi_version())
     _lib = L

@@ -211,25 +211,15 @@ int mups_index_bbox(const mups_index* ix, float min3_host[3], float max3_host[3]
 int64_t mups_index_size(const mups_index* ix) { return ix ? ix->n : 0; }
 
 // ---- half 1 -------------------------------------------------------------------------------------
+static int query_common(const char* what, const mups_index* ix, const int64_t* query_idx_dev, int64_t B, const double* r_abs_host,
+                        int S, int P, uint64_t seed, int32_t* nbr_idx_dev, int32_t* nbr_total_dev, float* patches_dev,
+                        int32_t* n_eff_dev, int32_t* nbr_pos_dev, cudaStream_t st);
+
 int mups_ball_query(const mups_index* ix, const int64_t* query_idx_dev, int64_t B, const double* r_abs_host, int S,
                     int P, uint64_t seed, int32_t* nbr_idx_dev, int32_t* nbr_total_dev, float* patches_dev,
                     int32_t* n_eff_dev, mups_stream stream) {
-    MUPS_REQUIRE(ix != nullptr, "mups_ball_query: index is NULL");
-    MUPS_REQUIRE(B >= 0 && B <= 0x7FFFFFFFll, "mups_ball_query: B=%lld out of range", (long long)B);
-    MUPS_REQUIRE(S >= 1 && S <= MUPS_MAX_SCALES, "mups_ball_query: S=%d out of range [1, %d]", S, MUPS_MAX_SCALES);
-    MUPS_REQUIRE(P >= 1 && P <= MUPS_MAX_POINTS_PER_PATCH, "mups_ball_query: P=%d out of range [1, %d]", P,
-                 MUPS_MAX_POINTS_PER_PATCH);
-    MUPS_REQUIRE(r_abs_host != nullptr, "mups_ball_query: radii are NULL");
-    for (int s = 0; s < S; ++s)
-        MUPS_REQUIRE(std::isfinite(r_abs_host[s]) && r_abs_host[s] >= 0.0, "mups_ball_query: radius %d is %g", s, r_abs_host[s]);
-    MUPS_REQUIRE(B == 0 || (query_idx_dev && n_eff_dev), "mups_ball_query: query_idx / n_eff is NULL");
-    if (int rc = check_device(ix->device, "mups_ball_query")) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (st != ix->build_stream) MUPS_CUDA_TRY(cudaStreamWaitEvent(st, ix->built, 0));
-    if (int rc = launch_ball_query(ix, query_idx_dev, B, r_abs_host, S, P, seed, nbr_idx_dev, nbr_total_dev, patches_dev,
-                                   n_eff_dev, nullptr, st))
-        return rc;
-    return note_use(ix, st);
+    return query_common("mups_ball_query", ix, query_idx_dev, B, r_abs_host, S, P, seed, nbr_idx_dev, nbr_total_dev, patches_dev,
+                        n_eff_dev, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 // ---- GMM ---------------------------------------------------------------------------------------
@@ -340,18 +330,17 @@ int mups_gmm_size(const mups_gmm* g) { return g ? g->G : 0; }
 int mups_gmm_is_separable(const mups_gmm* g) { return g ? g->separable : 0; }
 
 // ---- half 2 -------------------------------------------------------------------------------------
-int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_eff_dev, int64_t B, int S, int P,
-               uint32_t flags, float* out_dev, mups_stream stream) {
-    MUPS_REQUIRE(gmm != nullptr, "mups_3dmfv: gmm is NULL");
-    MUPS_REQUIRE(B >= 0, "mups_3dmfv: B=%lld is negative", (long long)B);
-    MUPS_REQUIRE(S >= 1 && S <= MUPS_MAX_SCALES, "mups_3dmfv: S=%d out of range [1, %d]", S, MUPS_MAX_SCALES);
-    MUPS_REQUIRE(P >= 1 && P <= MUPS_MAX_POINTS_PER_PATCH, "mups_3dmfv: P=%d out of range [1, %d]", P, MUPS_MAX_POINTS_PER_PATCH);
-    MUPS_REQUIRE(B == 0 || (patches_dev && out_dev), "mups_3dmfv: patches / out is NULL");
-    MUPS_REQUIRE(!(flags & MUPS_FLAG_MASKED) || B == 0 || n_eff_dev, "mups_3dmfv: n_eff is required with MUPS_FLAG_MASKED "
-                 "(the reference fails on n_original_points=None, tf_util.py:665)");
-    MUPS_REQUIRE((flags & ~(MUPS_FLAG_MASKED | MUPS_LAYOUT_CHANNEL | MUPS_FLAG_NO_FASTPATH | MUPS_FLAG_WIDE_STORES)) == 0, "mups_3dmfv: unknown flags 0x%x", flags);
-    if (int rc = check_device(gmm->device, "mups_3dmfv")) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int stats_common(const char* what, const mups_gmm* gmm, const float* patches_dev, const int32_t* n_eff_dev, int64_t B,
+                        int S, int P, uint32_t flags, float* out_dev, const GatherSource* src, cudaStream_t st) {
+    MUPS_REQUIRE(gmm != nullptr, "%s: gmm is NULL", what);
+    MUPS_REQUIRE(B >= 0, "%s: B=%lld is negative", what, (long long)B);
+    MUPS_REQUIRE(S >= 1 && S <= MUPS_MAX_SCALES, "%s: S=%d out of range [1, %d]", what, S, MUPS_MAX_SCALES);
+    MUPS_REQUIRE(P >= 1 && P <= MUPS_MAX_POINTS_PER_PATCH, "%s: P=%d out of range [1, %d]", what, P, MUPS_MAX_POINTS_PER_PATCH);
+    MUPS_REQUIRE(B == 0 || ((patches_dev || src) && out_dev), "%s: patches / out is NULL", what);
+    MUPS_REQUIRE(!(flags & MUPS_FLAG_MASKED) || B == 0 || n_eff_dev, "%s: n_eff is required with MUPS_FLAG_MASKED "
+                 "(the reference fails on n_original_points=None, tf_util.py:665)", what);
+    MUPS_REQUIRE((flags & ~(MUPS_FLAG_MASKED | MUPS_LAYOUT_CHANNEL | MUPS_FLAG_NO_FASTPATH | MUPS_FLAG_WIDE_STORES)) == 0, "%s: unknown flags 0x%x", what, flags);
+    if (int rc = check_device(gmm->device, what)) return rc;
     // stream-ordered scratch for the fast path's fallback worklist (1 counter + one id per (query, scale))
     int* work = nullptr;
     if (gmm->separable && !(flags & MUPS_FLAG_NO_FASTPATH) && B > 0)
@@ -360,19 +349,82 @@ int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_e
         if (int prc = library_pool(gmm->device, &pool)) return prc;
         MUPS_CUDA_TRY(cudaMallocFromPoolAsync((void**)&work, sizeof(int) * (size_t)(B * S + 1), pool, st));
     }
-    const int rc = launch_3dmfv(gmm, patches_dev, n_eff_dev, B, S, P, flags, out_dev, work, st);
+    const int rc = launch_3dmfv(gmm, patches_dev, n_eff_dev, B, S, P, flags, out_dev, work, src, st);
     if (work) cudaFreeAsync(work, st);
     return rc;
+}
+
+int mups_3dmfv(const mups_gmm* gmm, const float* patches_dev, const int32_t* n_eff_dev, int64_t B, int S, int P,
+               uint32_t flags, float* out_dev, mups_stream stream) {
+    return stats_common("mups_3dmfv", gmm, patches_dev, n_eff_dev, B, S, P, flags, out_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// ---- K6: selection hand-off (patches never in HBM) ------------------------------------------------------------------
+static int query_common(const char* what, const mups_index* ix, const int64_t* query_idx_dev, int64_t B, const double* r_abs_host,
+                        int S, int P, uint64_t seed, int32_t* nbr_idx_dev, int32_t* nbr_total_dev, float* patches_dev,
+                        int32_t* n_eff_dev, int32_t* nbr_pos_dev, cudaStream_t st) {
+    MUPS_REQUIRE(ix != nullptr, "%s: index is NULL", what);
+    MUPS_REQUIRE(B >= 0 && B <= 0x7FFFFFFFll, "%s: B=%lld out of range", what, (long long)B);
+    MUPS_REQUIRE(S >= 1 && S <= MUPS_MAX_SCALES, "%s: S=%d out of range [1, %d]", what, S, MUPS_MAX_SCALES);
+    MUPS_REQUIRE(P >= 1 && P <= MUPS_MAX_POINTS_PER_PATCH, "%s: P=%d out of range [1, %d]", what, P, MUPS_MAX_POINTS_PER_PATCH);
+    MUPS_REQUIRE(r_abs_host != nullptr, "%s: radii are NULL", what);
+    for (int s = 0; s < S; ++s)
+        MUPS_REQUIRE(std::isfinite(r_abs_host[s]) && r_abs_host[s] >= 0.0, "%s: radius %d is %g", what, s, r_abs_host[s]);
+    MUPS_REQUIRE(B == 0 || (query_idx_dev && n_eff_dev), "%s: query_idx / n_eff is NULL", what);
+    if (int rc = check_device(ix->device, what)) return rc;
+    if (st != ix->build_stream) MUPS_CUDA_TRY(cudaStreamWaitEvent(st, ix->built, 0));
+    if (int rc = launch_ball_query(ix, query_idx_dev, B, r_abs_host, S, P, seed, nbr_idx_dev, nbr_total_dev, patches_dev,
+                                   n_eff_dev, nbr_pos_dev, st))
+        return rc;
+    return note_use(ix, st);
+}
+
+int mups_ball_query_select(const mups_index* index, const int64_t* query_idx_dev, int64_t B, const double* r_abs_host, int S,
+                           int P, uint64_t seed, int32_t* nbr_pos_dev, int32_t* nbr_total_dev, int32_t* n_eff_dev,
+                           mups_stream stream) {
+    MUPS_REQUIRE(B == 0 || nbr_pos_dev, "mups_ball_query_select: nbr_pos is NULL");
+    return query_common("mups_ball_query_select", index, query_idx_dev, B, r_abs_host, S, P, seed, nullptr, nbr_total_dev, nullptr,
+                        n_eff_dev, nbr_pos_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mups_3dmfv_selected(const mups_gmm* gmm, const mups_index* index, const int64_t* query_idx_dev, int64_t B,
+                        const double* r_abs_host, int S, int P, const int32_t* nbr_pos_dev, const int32_t* n_eff_dev,
+                        uint32_t flags, float* out_dev, mups_stream stream) {
+    MUPS_REQUIRE(index != nullptr, "mups_3dmfv_selected: index is NULL");
+    MUPS_REQUIRE(r_abs_host != nullptr, "mups_3dmfv_selected: radii are NULL");
+    MUPS_REQUIRE(B == 0 || (query_idx_dev && nbr_pos_dev), "mups_3dmfv_selected: query_idx / nbr_pos is NULL");
+    if (int rc = check_device(index->device, "mups_3dmfv_selected")) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (st != index->build_stream) MUPS_CUDA_TRY(cudaStreamWaitEvent(st, index->built, 0));
+    GatherSource src{index, query_idx_dev, nbr_pos_dev, r_abs_host};
+    if (int rc = stats_common("mups_3dmfv_selected", gmm, nullptr, n_eff_dev, B, S, P, flags | MUPS_FLAG_MASKED, out_dev, &src, st))
+        return rc;
+    return note_use(index, st);
 }
 
 int mups_features(const mups_index* index, const mups_gmm* gmm, const int64_t* query_idx_dev, int64_t B,
                   const double* r_abs_host, int S, int P, uint64_t seed, uint32_t flags, float* patches_dev,
                   int32_t* n_eff_dev, int32_t* nbr_total_dev, float* out_dev, mups_stream stream) {
-    MUPS_REQUIRE(B == 0 || patches_dev, "mups_features: patches scratch is NULL");
-    int rc = mups_ball_query(index, query_idx_dev, B, r_abs_host, S, P, seed, nullptr, nbr_total_dev, patches_dev,
-                             n_eff_dev, stream);
-    if (rc) return rc;
-    return mups_3dmfv(gmm, patches_dev, n_eff_dev, B, S, P, flags | MUPS_FLAG_MASKED, out_dev, stream);
+    if (patches_dev) {
+        int rc = mups_ball_query(index, query_idx_dev, B, r_abs_host, S, P, seed, nullptr, nbr_total_dev, patches_dev,
+                                 n_eff_dev, stream);
+        if (rc) return rc;
+        return mups_3dmfv(gmm, patches_dev, n_eff_dev, B, S, P, flags | MUPS_FLAG_MASKED, out_dev, stream);
+    }
+    // K6: no patch tensor.  The ball query hands over the positions of the selected neighbours (4 bytes per slot, library
+    // scratch); the statistics kernel gathers, centres and normalises them while it stages a patch.
+    MUPS_REQUIRE(index != nullptr, "mups_features: index is NULL");
+    if (B <= 0 || S < 1 || S > MUPS_MAX_SCALES || P < 1 || P > MUPS_MAX_POINTS_PER_PATCH)       // let the callee report it
+        return mups_ball_query_select(index, query_idx_dev, B, r_abs_host, S, P, seed, nullptr, nbr_total_dev, n_eff_dev, stream);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemPool_t pool = nullptr;
+    if (int rc = library_pool(index->device, &pool)) return rc;
+    int32_t* pos = nullptr;
+    MUPS_CUDA_TRY(cudaMallocFromPoolAsync((void**)&pos, sizeof(int32_t) * (size_t)B * S * P, pool, st));
+    int rc = mups_ball_query_select(index, query_idx_dev, B, r_abs_host, S, P, seed, pos, nbr_total_dev, n_eff_dev, stream);
+    if (!rc) rc = mups_3dmfv_selected(gmm, index, query_idx_dev, B, r_abs_host, S, P, pos, n_eff_dev, flags, out_dev, stream);
+    cudaFreeAsync(pos, st);
+    return rc;
 }
 
 }  // extern "C"

@@ -117,8 +117,15 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
                       int32_t* nbr_pos, cudaStream_t st);
 // in-place exclusive scan of n uint32 counters; tile_sums: scratch of (n + 2047) / 2048 entries
 int launch_exclusive_scan(uint32_t* data, int64_t n, uint32_t* tile_sums, cudaStream_t st);
+// K6: where the statistics kernel finds the patch points when no patch tensor exists
+struct GatherSource {
+    const mups_index* index;
+    const int64_t* q;          // [B] centre indices (device)
+    const int32_t* nbr_pos;    // [B,S,P] positions in index->sorted (device), -1 beyond n_eff
+    const double* r_abs;       // [S] absolute radii (host)
+};
 int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff, int64_t B, int S, int P,
-                 uint32_t flags, float* out, int* work, cudaStream_t st);
+                 uint32_t flags, float* out, int* work, const GatherSource* src, cudaStream_t st);
 
 // ---- small device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t morton_expand(uint32_t v) {  // 10 bits -> every third bit

@@ -24,6 +24,7 @@
 // candidates, and the P smallest keys are resolved among those few; anything this cannot decide is handed to the
 // flat kernel through a worklist, so the result is the same function of (seed, centre, scale, index set).
 #include <cmath>
+#include <cstdlib>
 
 #include "mups_common.cuh"
 
@@ -52,6 +53,8 @@ struct QueryArgs {
     float r2_lo[MUPS_MAX_SCALES];   // fp32 guard band around r2: below -> inside, above hi -> outside
     float r2_hi[MUPS_MAX_SCALES];
     float rf[MUPS_MAX_SCALES];      // float32(r): the divisor of pcpnet_dataset.py:343
+    int orig[MUPS_MAX_SCALES];      // the kernels see the radii in ASCENDING order (nested balls); orig[s] = the caller's scale index:
+                                    // it salts the selection (Philox counter) and addresses the output rows
     float r_max;
     float r2_hi_max;
     uint32_t k0, k1;                // philox key = seed
@@ -357,6 +360,7 @@ __device__ __forceinline__ void finish_patch(const QueryArgs& a, const QueryCtx&
         const uint32_t ne = min(total, (uint32_t)P);
         const unsigned long long* v = sel + (size_t)s * Ppad;
         const float rf = a.rf[s];
+        const int os = a.orig[s];                           // output row of this radius
         for (uint32_t t = tid; t < (uint32_t)P; t += NT) {
             float ox = 0.f, oy = 0.f, oz = 0.f;
             int32_t id = -1, ps = -1;
@@ -372,15 +376,15 @@ __device__ __forceinline__ void finish_patch(const QueryArgs& a, const QueryCtx&
                 }
             }
             if (a.patches) {
-                float* o = a.patches + ((b * S + s) * (int64_t)P + t) * 3;
+                float* o = a.patches + ((b * S + os) * (int64_t)P + t) * 3;
                 o[0] = ox; o[1] = oy; o[2] = oz;
             }
-            if (a.nbr_idx) a.nbr_idx[(b * S + s) * (int64_t)P + t] = id;
-            if (a.nbr_pos) a.nbr_pos[(b * S + s) * (int64_t)P + t] = ps;
+            if (a.nbr_idx) a.nbr_idx[(b * S + os) * (int64_t)P + t] = id;
+            if (a.nbr_pos) a.nbr_pos[(b * S + os) * (int64_t)P + t] = ps;
         }
         if (tid == 0) {
-            a.n_eff[b * S + s] = (int32_t)ne;
-            if (a.nbr_total) a.nbr_total[b * S + s] = (int32_t)total;
+            a.n_eff[b * S + os] = (int32_t)ne;
+            if (a.nbr_total) a.nbr_total[b * S + os] = (int32_t)total;
         }
     }
 }
@@ -448,7 +452,7 @@ __device__ __forceinline__ void ball_query_flat_one(const QueryArgs& a, const in
     int R_unused;
     load_centre(a, q, c, &R_unused);
     if (tid < S) {   // per-patch randomness: one Philox call per radius
-        const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)tid, 0u, 0u, a.k0, a.k1);
+        const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)a.orig[tid], 0u, 0u, a.k0, a.k1);
         salt.a[tid] = w.x;
         salt.b[tid] = w.y | 1u;
     }
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(kHT, 3) ball_query_hier_kernel(const QueryArgs
     int R;
     load_centre(a, q, c, &R);
     if (tid < S) {
-        const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)tid, 0u, 0u, a.k0, a.k1);
+        const uint4 w = philox4x32_10((uint32_t)q, (uint32_t)a.orig[tid], 0u, 0u, a.k0, a.k1);
         salt.a[tid] = w.x;
         salt.b[tid] = w.y | 1u;
     }
@@ -1069,8 +1073,13 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
     a.fuse = (uint32_t)g_fuse_candidates.load();
     double rmax = 0.0;
     float hi_max = 0.f;
+    int ord[MUPS_MAX_SCALES];
+    for (int s = 0; s < MUPS_MAX_SCALES; ++s) ord[s] = s;
+    for (int i = 1; i < S; ++i)                                  // stable insertion sort of the scales by radius
+        for (int j = i; j > 0 && r_abs[ord[j]] < r_abs[ord[j - 1]]; --j) { const int t = ord[j]; ord[j] = ord[j - 1]; ord[j - 1] = t; }
     for (int s = 0; s < MUPS_MAX_SCALES; ++s) {
-        const double r = s < S ? r_abs[s] : 0.0;
+        a.orig[s] = ord[s];
+        const double r = s < S ? r_abs[ord[s]] : 0.0;
         a.r2[s] = r * r;
         a.r2_lo[s] = (float)(a.r2[s] * (1.0 - 4e-6));
         a.r2_hi[s] = (float)(a.r2[s] * (1.0 + 4e-6));
@@ -1144,6 +1153,12 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
             MUPS_LAUNCH_QUERY(ball_query_hier_kernel, 7, B, kHT, smem_h) MUPS_LAUNCH_QUERY(ball_query_hier_kernel, 8, B, kHT, smem_h)
         }
         MUPS_CHECK_LAUNCH();
+        if (getenv("MUPS_DEBUG_WORKLIST")) {              // diagnostics only: synchronises
+            int32_t handed = -1;
+            cudaMemcpyAsync(&handed, a.work_count, sizeof(handed), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            fprintf(stderr, "[mups] hierarchical ball query: %d of %lld rows handed to the flat kernel\n", handed, (long long)B);
+        }
         // the rows it could not decide (statistical tail of the key threshold): the flat kernel, persistent over the worklist
         a.order = nullptr;
         const int64_t grid = B < 2 * kNumSMs ? B : 2 * kNumSMs;

@@ -50,7 +50,29 @@ struct StatsArgs {
     int* work_count;           // [1]
     int use_worklist;          // general kernel: take items from the worklist
     int gmm_in_smem;           // general kernel: stage A / Bv in shared memory (else read them through L1/L2)
+    // K6: patches never materialise -- the staging step gathers the selected neighbours from the index and centres /
+    // normalises them itself (same __fsub_rn / __fdiv_rn as K4: bit-identical to reading the patch tensor)
+    const float4* g_sorted;    // index->sorted, or nullptr: read `patches`
+    const int32_t* g_pos_of;   // index->pos_of
+    const int64_t* g_q;        // [B] centre indices
+    const int32_t* g_pos;      // [B,S,P] positions in `sorted` of the selected neighbours, -1 beyond n_eff
+    int64_t g_n;               // points in the index
+    float g_rf[MUPS_MAX_SCALES];   // float32(r_s): the divisor of pcpnet_dataset.py:343
 };
+
+// One patch slot (query b, scale s, slot t) of the K6 path: (p - c) / float32(r) in IEEE fp32, zeros beyond n_eff.
+__device__ __forceinline__ float3 gathered_point(const StatsArgs& a, int64_t b, int s, int t, const float4& c) {
+    const int32_t ps = __ldg(a.g_pos + (b * a.S + s) * (int64_t)a.P + t);
+    if (ps < 0) return make_float3(0.f, 0.f, 0.f);
+    const float4 p = __ldg(a.g_sorted + ps);
+    const float rf = a.g_rf[s];
+    return make_float3(__fdiv_rn(__fsub_rn(p.x, c.x), rf), __fdiv_rn(__fsub_rn(p.y, c.y), rf), __fdiv_rn(__fsub_rn(p.z, c.z), rf));
+}
+__device__ __forceinline__ float4 gather_centre(const StatsArgs& a, int64_t b) {
+    const int64_t q = a.g_q[b];
+    if (q < 0 || q >= a.g_n) return make_float4(0.f, 0.f, 0.f, 0.f);      // invalid centre: the ball query left an empty row
+    return __ldg(a.g_sorted + __ldg(a.g_pos_of + q));
+}
 
 typedef unsigned long long u64;
 
@@ -198,7 +220,13 @@ __global__ void __launch_bounds__(NT) stats_general_kernel(const StatsArgs a) {
         if (n_eff < 0) n_eff = 0;
         const int m = masked ? min(n_eff + 1, P) : P;     // slots with r > n_eff are masked (tf_util.py:696)
         const bool any_masked = m < P;
-        {
+        if (a.g_sorted) {
+            const float4 cq = gather_centre(a, b);
+            for (int n = tid; n < m; n += NT) {
+                const float3 v = gathered_point(a, b, s, n, cq);
+                pt[n] = make_float4(v.x, v.y, v.z, 0.f);
+            }
+        } else {
             const float* src = a.patches + (b * S + s) * (int64_t)P * 3;
             for (int n = tid; n < m; n += NT)
                 pt[n] = make_float4(__ldg(src + 3 * n), __ldg(src + 3 * n + 1), __ldg(src + 3 * n + 2), 0.f);
@@ -396,10 +424,17 @@ __global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_ke
     if (n_eff < 0) n_eff = 0;
     const int m = masked ? min(n_eff + 1, P) : P;       // slots with r > n_eff are masked (tf_util.py:696)
     const bool any_masked = m < P;
-    const float* src = a.patches + (b * S + s) * (int64_t)P * 3;
-
     for (int i = tid; i < 3 * 64; i += NT) lat[i] = __ldg(a.axis_mu + i);
-    for (int i = tid; i < 3 * m; i += NT) coords[i] = __ldg(src + i);
+    if (a.g_sorted) {
+        const float4 cq = gather_centre(a, b);
+        for (int t = tid; t < m; t += NT) {
+            const float3 v = gathered_point(a, b, s, t, cq);
+            coords[3 * t] = v.x; coords[3 * t + 1] = v.y; coords[3 * t + 2] = v.z;
+        }
+    } else {
+        const float* src = a.patches + (b * S + s) * (int64_t)P * 3;
+        for (int i = tid; i < 3 * m; i += NT) coords[i] = __ldg(src + i);
+    }
     if (tid < 3) { axis_par[4 * tid] = a.isig[tid]; axis_par[4 * tid + 1] = a.guard_lo[tid]; axis_par[4 * tid + 2] = a.guard_hi[tid]; }
     if (tid == 0) s_fallback = 0;
 
@@ -752,8 +787,16 @@ static int dispatch_general(const StatsArgs& a, int64_t items, int grid, cudaStr
 static bool pow2_in(int v, int lo, int hi) { return v >= lo && v <= hi && (v & (v - 1)) == 0; }
 
 int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff, int64_t B, int S, int P,
-                 uint32_t flags, float* out, int* work /* [1 + B*S] ints of scratch, or nullptr */, cudaStream_t st) {
+                 uint32_t flags, float* out, int* work /* [1 + B*S] ints of scratch, or nullptr */, const GatherSource* src,
+                 cudaStream_t st) {
     StatsArgs a;
+    a.g_sorted = nullptr; a.g_pos_of = nullptr; a.g_q = nullptr; a.g_pos = nullptr; a.g_n = 0;
+    for (int k = 0; k < MUPS_MAX_SCALES; ++k) a.g_rf[k] = 1.0f;
+    if (src) {
+        a.g_sorted = src->index->sorted; a.g_pos_of = src->index->pos_of; a.g_n = src->index->n;
+        a.g_q = src->q; a.g_pos = src->nbr_pos;
+        for (int k = 0; k < S; ++k) a.g_rf[k] = (float)src->r_abs[k];
+    }
     a.A = gmm->A; a.Bv = gmm->Bv; a.C = gmm->C; a.G = gmm->G;
     a.patches = patches; a.n_eff = n_eff; a.S = S; a.P = P; a.flags = flags & ~MUPS_FLAG_NO_FASTPATH; a.out = out;
     a.axis_mu = gmm->axis_mu;

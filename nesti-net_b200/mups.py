@@ -212,6 +212,23 @@ class PointIndex(object):
             return patches, n_eff, total, nbr
         return patches, n_eff, total
 
+    def select(self, query_idx, radii_abs, points_per_patch, seed=3627473):
+        """Half 1 without the patch tensor (mups_ball_query_select): (nbr_pos [B,S,P] i32 -- opaque positions for
+        ``stats_3dmfv_selected`` --, n_eff [B,S] i32, nbr_total [B,S] i32)."""
+        dev = self.device
+        q = _as_device(query_idx, torch.int64, dev).reshape(-1)
+        B, S, P = int(q.shape[0]), len(radii_abs), int(points_per_patch)
+        r = np.ascontiguousarray(np.asarray(radii_abs, dtype=np.float64))
+        pos = torch.empty((B, S, P), dtype=torch.int32, device=dev)
+        n_eff = torch.empty((B, S), dtype=torch.int32, device=dev)
+        total = torch.empty((B, S), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().mups_ball_query_select(
+                self._h, ctypes.c_void_p(q.data_ptr()), B, r.ctypes.data_as(_F64P), S, P, int(seed) & (2 ** 64 - 1),
+                ctypes.c_void_p(pos.data_ptr()), ctypes.c_void_p(total.data_ptr()), ctypes.c_void_p(n_eff.data_ptr()),
+                _stream_ptr(dev)), "mups_ball_query_select")
+        return pos, n_eff, total
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
@@ -272,14 +289,37 @@ def stats_3dmfv(patches, n_eff, gmm, n_scales, masked=True, layout="mups", out=N
     return out
 
 
+def stats_3dmfv_selected(index, gmm, query_idx, radii_abs, nbr_pos, n_eff, out=None, fastpath=True):
+    """3DmFV statistics of the patches a selection (PointIndex.select) describes, gathered from the index by the
+    statistics kernel itself (mups_3dmfv_selected): MuPS [B,res,res,res,20*S]."""
+    dev = index.device
+    q = _as_device(query_idx, torch.int64, dev).reshape(-1)
+    B, S, P, G = int(nbr_pos.shape[0]), int(nbr_pos.shape[1]), int(nbr_pos.shape[2]), gmm.G
+    r = np.ascontiguousarray(np.asarray(radii_abs, dtype=np.float64))
+    res = int(round(G ** (1.0 / 3.0)))
+    shape = (B, res, res, res, 20 * S) if res ** 3 == G else (B, G, 20 * S)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
+    elif out.numel() != B * S * 20 * G or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 CUDA tensor of %d elements" % (B * S * 20 * G))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().mups_3dmfv_selected(
+            gmm.handle, index.handle, ctypes.c_void_p(q.data_ptr()), B, r.ctypes.data_as(_F64P), S, P,
+            ctypes.c_void_p(nbr_pos.data_ptr()), ctypes.c_void_p(n_eff.data_ptr()), 0 if fastpath else _lib.FLAG_NO_FASTPATH,
+            ctypes.c_void_p(out.data_ptr()), _stream_ptr(dev)), "mups_3dmfv_selected")
+    return out
+
+
 def mups_features(index, gmm, query_idx, radii_abs, points_per_patch, seed=3627473, out=None,
                   return_patches=False, fastpath=True):
-    """Both halves for a batch of centres: MuPS [B,res,res,res,20*S] (mups_features)."""
+    """Both halves for a batch of centres: MuPS [B,res,res,res,20*S] (mups_features).  Without ``return_patches`` no
+    patch tensor exists anywhere (K6: the ball query hands the statistics kernel the positions of the selected
+    neighbours); the features are the same bit for bit."""
     dev = index.device
     q = _as_device(query_idx, torch.int64, dev).reshape(-1)
     B, S, P, G = int(q.shape[0]), len(radii_abs), int(points_per_patch), gmm.G
     r = np.ascontiguousarray(np.asarray(radii_abs, dtype=np.float64))
-    patches = torch.empty((B, S * P, 3), dtype=torch.float32, device=dev)
+    patches = torch.empty((B, S * P, 3), dtype=torch.float32, device=dev) if return_patches else None
     n_eff = torch.empty((B, S), dtype=torch.int32, device=dev)
     total = torch.empty((B, S), dtype=torch.int32, device=dev)
     res = int(round(G ** (1.0 / 3.0)))
@@ -292,8 +332,9 @@ def mups_features(index, gmm, query_idx, radii_abs, points_per_patch, seed=36274
     with torch.cuda.device(dev):
         _lib.check(_lib.load().mups_features(
             index.handle, gmm.handle, ctypes.c_void_p(q.data_ptr()), B, r.ctypes.data_as(_F64P), S, P,
-            int(seed) & (2 ** 64 - 1), flags, ctypes.c_void_p(patches.data_ptr()), ctypes.c_void_p(n_eff.data_ptr()),
-            ctypes.c_void_p(total.data_ptr()), ctypes.c_void_p(out.data_ptr()), _stream_ptr(dev)), "mups_features")
+            int(seed) & (2 ** 64 - 1), flags, ctypes.c_void_p(patches.data_ptr() if patches is not None else 0),
+            ctypes.c_void_p(n_eff.data_ptr()), ctypes.c_void_p(total.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+            _stream_ptr(dev)), "mups_features")
     if return_patches:
         return out, patches, n_eff, total
     return out
