@@ -158,6 +158,23 @@ int mups_features(const mups_index* index, const mups_gmm* gmm, const int64_t* q
                   float* patches_dev, int32_t* n_eff_dev, int32_t* nbr_total_dev, float* out_dev,
                   mups_stream stream);
 
+/* ---- the consumer on the tensor cores (replaces the TF layers of models/experts_n_est.py:155-314) ---- */
+/* MuPS fp32 [rows, 20 S] (rows = B * res^3, as mups_3dmfv wrote it) -> bf16 [rows, 32 S]: each scale's 20 channels padded
+ * to 32, the activation layout of the kernels below (channel slices of the single-scale experts 16-byte aligned). */
+int mups_moe_pack_input(const float* mups_dev, int64_t rows, int S, void* out_bf16_dev, mups_stream stream);
+/* tf_util.conv3d (utils/tf_util.py:254-311: stride 1, 'SAME', bias, batch norm, ReLU) and tf_util.fully_connected
+ * (:314-351; D = 1, k = 1) as one tcgen05 implicit GEMM:
+ *   y[b,z,y,x,co] = act(scale[co] * sum_{dz,dy,dx,ci} x[b, z+dz-p, y+dy-p, x+dx-p, cin_off+ci] * w[(dz*k+dy)*k+dx][co][ci] + shift[co])
+ * x_bf16_dev: NDHWC bf16 [B, D, D, D, cin_total] (D in {1, 2, 4, 8}); channels [cin_off, cin_off + cin) are read, zero outside the
+ * volume with p = (k - 1) / 2 cells before (TF 'SAME': the smaller half first).  w_bf16_dev: [k^3][cout][cin_w] bf16.
+ * scale / shift: [cout] fp32 (bias and the batch norm's moving statistics folded by the caller); relu: 0 / 1.
+ * Output: bf16 into channels [cout_off, cout_off + cout) of y_bf16_dev [B, D, D, D, cout_total] (NULL to skip) and / or
+ * fp32 [B*D^3, cout] into y_f32_dev (NULL to skip).  Channel counts: cin, cin_total, cin_off, cin_w, cout_total, cout_off
+ * multiples of 8, cout a multiple of 16.  bf16 products, fp32 accumulation (tensor memory). */
+int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin,
+                        const void* w_bf16_dev, int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev,
+                        int relu, void* y_bf16_dev, int cout_total, int cout_off, float* y_f32_dev, mups_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ from . import _lib  # noqa: F401
 from .mups import (GMMHandle, GridGMM, PointIndex, get_3d_grid_gmm, gmm_handle, mups_features,  # noqa: F401
                    stats_3dmfv, stats_3dmfv_selected)
 from . import tf_util, experts_n_est, experts_net, pcpnet_dataset, provider, dist, pipeline  # noqa: F401
-from . import evaluate, inference  # noqa: F401
+from . import evaluate, inference, moe_engine  # noqa: F401
 from .pipeline import MuPSPipeline  # noqa: F401
 
 __all__ = ["GMMHandle", "GridGMM", "PointIndex", "get_3d_grid_gmm", "gmm_handle", "mups_features",

@@ -1,0 +1,334 @@
+// Consumer of the MuPS tensor: the 3D-Inception / Mixture-of-Experts convolutions of
+// models/experts_n_est.py:155-314 (tf_util.conv3d :254-311 and fully_connected :314-351, both with batch norm and ReLU)
+// as ONE hand-written implicit-GEMM kernel on the 5th-generation tensor cores:
+//
+//   y[b, z, y, x, co] = act( scale[co] * sum_{dz,dy,dx,ci} x[b, z+dz-p, y+dy-p, x+dx-p, ci] * w[dz,dy,dx][co][ci] + shift[co] )
+//
+// * GEMM view: M = voxels (tile of 128 = two z-slices of an 8^3 volume, two whole 4^3 volumes, sixteen 2^3 volumes or 128
+//   flattened rows of a fully connected layer), N = output channels (tile <= 256), K = taps x input channels (64 per stage).
+// * A operand: one TMA load per (tap, 64-channel block) of the NDHWC bf16 activations through a 5-D tiled tensor map whose box
+//   is (64 channels, W, H, dz-box, batch-box); the tap only shifts the box coordinates and the TMA unit zero-fills what falls
+//   outside the volume -- TF 'SAME' padding (asymmetric for even kernels: the smaller half first) without an im2col buffer
+//   and without a single predicate.  The box lands in shared memory as 128 rows of 128 bytes in the 128-byte-swizzled K-major
+//   layout tcgen05.mma reads.
+// * B operand: weights [tap][Cout][Cin] bf16 through a 3-D tensor map, same layout.
+// * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one elected thread, accumulator in tensor memory (128 lanes x N
+//   columns), tcgen05.commit arrives on the mbarriers that free the shared-memory stage / announce the finished accumulator.
+// * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (tcgen05.ld 32 lanes x 32 columns each, folded
+//   bias + batch norm as scale / shift, ReLU, bf16 pack, 16-byte stores into a channel slice of the NDHWC output, so the
+//   inception module's concat costs nothing).
+// Every mbarrier wait is bounded: a barrier that never completes traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "mups_common.cuh"
+
+namespace mups {
+
+constexpr int kConvThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kTileK = 64;                 // bf16 elements per stage = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kTileK * 2;
+constexpr int kTmemCols = 256;
+constexpr int kMaxStages = 8;
+
+struct ConvArgs {
+    int B, D, k, pl;                 // batch, volume edge, kernel edge, padding before (TF 'SAME': (k - 1) / 2)
+    int kblocks;                     // ceil(Cin / 64)
+    int n_tile;                      // output channels per CTA (multiple of 16, <= 256)
+    int stages;
+    int dz_box, b_box;               // z-slices / samples per 128-voxel tile
+    int Cout;                        // output channels of this launch (rows of the weight tensor per tap)
+    const float* scale;              // [Cout]
+    const float* shift;              // [Cout]
+    int relu;
+    __nv_bfloat16* y;                // NDHWC
+    long long y_stride;              // channels per voxel of the output tensor
+    int cout_off;                    // first output channel written
+    float* y_f32;                    // optional fp32 output [rows, Cout] (last layers), or nullptr
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: ~2^22 probes (each probe itself blocks for a hardware-defined interval) before giving up
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// K-major, 128-byte swizzle: 8-row atoms of 1024 bytes, SBO = 1024; version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    // 1024-byte alignment of the stages (the swizzle pattern is a function of the shared-memory address bits)
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.n_tile * kTileK * 2;
+    const int stage_bytes = kABytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);      // full[stages], empty[stages], accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages), bar_acc = smem_u32(bars + 2 * kMaxStages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this CTA's tile: 128 voxels x n_tile output channels
+    const int tile_m = blockIdx.x, n0 = blockIdx.y * a.n_tile;
+    const int tiles_per_sample = (a.D * a.D * a.D + kTileM - 1) / kTileM;          // 4 for 8^3, else 1
+    const int b0 = tiles_per_sample > 1 ? tile_m / tiles_per_sample : tile_m * a.b_box;
+    const int z0 = tiles_per_sample > 1 ? (tile_m % tiles_per_sample) * a.dz_box : 0;
+    const int taps = a.k * a.k * a.k;
+    const int iters = taps * a.kblocks;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % a.stages;
+                mbar_wait(bar_empty + 8 * s, ((it / a.stages) & 1) ^ 1);
+                const int tap = it / a.kblocks, kb = it - tap * a.kblocks;
+                const int dz = tap / (a.k * a.k), dy = (tap / a.k) % a.k, dx = tap % a.k;
+                const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_expect_tx(bar_full + 8 * s, (uint32_t)stage_bytes);
+                tma_load_5d(dst, &map_x, bar_full + 8 * s, kb * kTileK, dx - a.pl, dy - a.pl, z0 + dz - a.pl, b0);
+                tma_load_3d(dst + kABytes, &map_w, bar_full + 8 * s, kb * kTileK, n0, tap);
+            }
+        }
+    } else if (warp == 1) {
+        // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % a.stages;
+            mbar_wait(bar_full + 8 * s, (it / a.stages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t da = umma_desc(sa), db = umma_desc(sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k)       // UMMA_K = 16 bf16 = 32 bytes: +2 in the descriptor's 16-byte units
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit(bar_empty + 8 * s);              // frees the stage once these MMAs have read it
+                if (it == iters - 1) umma_commit(bar_acc);   // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32 (w % 4), +32)
+        mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;                 // row of the tile = voxel in box order (w fastest, then h, z, sample)
+        const int W = a.D, HW = a.D * a.D;
+        const int x = m % W, yy = (m / W) % a.D, zl = (m / HW) % a.dz_box, bl = m / (HW * a.dz_box);
+        const long long bsample = (long long)b0 + bl;
+        const bool live = bsample < a.B;
+        const long long voxel = ((bsample * a.D + (z0 + zl)) * a.D + yy) * a.D + x;
+        __nv_bfloat16* yrow = a.y ? a.y + voxel * a.y_stride + a.cout_off + n0 : nullptr;
+        float* frow = a.y_f32 ? a.y_f32 + voxel * (long long)a.Cout + n0 : nullptr;
+        for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int co = n0 + c0 + j;
+                const float sc = co < a.Cout ? __ldg(a.scale + co) : 0.f, sh = co < a.Cout ? __ldg(a.shift + co) : 0.f;
+                float t = fmaf(__uint_as_float(v[j]), sc, sh);
+                f[j] = a.relu ? fmaxf(t, 0.f) : t;
+            }
+            if (live) {
+                if (yrow) {
+                    uint4 lo, hi;
+                    __nv_bfloat162 p;
+                    p = __floats2bfloat162_rn(f[0], f[1]);   lo.x = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[2], f[3]);   lo.y = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[4], f[5]);   lo.z = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[6], f[7]);   lo.w = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[8], f[9]);   hi.x = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[10], f[11]); hi.y = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[12], f[13]); hi.z = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[14], f[15]); hi.w = *reinterpret_cast<uint32_t*>(&p);
+                    uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+                    dst[0] = lo;
+                    dst[1] = hi;
+                }
+                if (frow) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c0 + j < a.Cout) frow[c0 + j] = f[j];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// MuPS fp32 [B, G, 20 S] -> bf16 [B, G, 32 S]: every scale's 20 channels padded to 32 (16-byte aligned channel slices for
+// the single-scale experts' tensor maps; the pad channels meet zero weights)
+__global__ void __launch_bounds__(256) pack_mups_bf16_kernel(const float* __restrict__ in, long long rows, int S, __nv_bfloat16* __restrict__ out) {
+    const long long n = rows * S * 32;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 31);
+        const long long rs = i >> 5;                       // row * S + scale
+        out[i] = __float2bfloat16_rn(c < 20 ? __ldg(in + rs * 20 + c) : 0.f);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+}  // namespace mups
+
+using namespace mups;
+
+extern "C" {
+
+int mups_moe_pack_input(const float* mups_dev, int64_t rows, int S, void* out_bf16_dev, mups_stream stream) {
+    MUPS_REQUIRE(rows >= 0 && S >= 1 && S <= MUPS_MAX_SCALES, "mups_moe_pack_input: rows=%lld, S=%d out of range", (long long)rows, S);
+    MUPS_REQUIRE(rows == 0 || (mups_dev && out_bf16_dev), "mups_moe_pack_input: NULL buffer");
+    if (rows == 0) return MUPS_OK;
+    const long long n = (long long)rows * S * 32;
+    const int grid = (int)((n + 255) / 256 < 16 * kNumSMs ? (n + 255) / 256 : 16 * kNumSMs);
+    pack_mups_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mups_dev, rows, S, static_cast<__nv_bfloat16*>(out_bf16_dev));
+    MUPS_CHECK_LAUNCH();
+    return MUPS_OK;
+}
+
+int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
+                        int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
+                        int cout_total, int cout_off, float* y_f32_dev, mups_stream stream) {
+    MUPS_REQUIRE(x_bf16_dev && w_bf16_dev && scale_dev && shift_dev && (y_bf16_dev || y_f32_dev), "mups_conv3d_bn_relu: NULL buffer");
+    MUPS_REQUIRE(B >= 1 && B < (1ll << 30), "mups_conv3d_bn_relu: B=%lld out of range", (long long)B);
+    MUPS_REQUIRE(D == 1 || D == 2 || D == 4 || D == 8, "mups_conv3d_bn_relu: volume edge %d (1, 2, 4 or 8)", D);
+    MUPS_REQUIRE(k >= 1 && k <= 5 && (D > 1 || k == 1), "mups_conv3d_bn_relu: kernel edge %d", k);
+    MUPS_REQUIRE(cin >= 8 && cin % 8 == 0 && cin_total % 8 == 0 && cin_off % 8 == 0 && cin_off + cin <= cin_total,
+                 "mups_conv3d_bn_relu: input channels (%d of %d at %d) must be multiples of 8", cin, cin_total, cin_off);
+    MUPS_REQUIRE(cin_w >= cin && cin_w % 8 == 0, "mups_conv3d_bn_relu: weight inner dimension %d", cin_w);
+    MUPS_REQUIRE(cout >= 16 && cout % 16 == 0, "mups_conv3d_bn_relu: output channels %d must be a multiple of 16", cout);
+    MUPS_REQUIRE(!y_bf16_dev || (cout_total % 8 == 0 && cout_off % 8 == 0 && cout_off + cout <= cout_total),
+                 "mups_conv3d_bn_relu: output channel slice (%d of %d at %d)", cout, cout_total, cout_off);
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("mups_conv3d_bn_relu: cuTensorMapEncodeTiled is not available (driver too old?)"); return MUPS_ERR_CUDA; }
+
+    ConvArgs a;
+    a.B = (int)B; a.D = D; a.k = k; a.pl = (k - 1) / 2;
+    a.kblocks = (cin + kTileK - 1) / kTileK;
+    int n_tile = cout;
+    if (n_tile > 256) { n_tile = 256; while (cout % n_tile) n_tile -= 16; }
+    a.n_tile = n_tile;
+    const int vox = D * D * D;
+    a.dz_box = vox >= kTileM ? kTileM / (D * D) : D;
+    a.b_box = vox >= kTileM ? 1 : kTileM / vox;
+    a.Cout = cout;
+    a.scale = scale_dev; a.shift = shift_dev; a.relu = relu;
+    a.y = static_cast<__nv_bfloat16*>(y_bf16_dev); a.y_stride = cout_total; a.cout_off = cout_off; a.y_f32 = y_f32_dev;
+    const int stage_bytes = kABytes + n_tile * kTileK * 2;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    a.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * kMaxStages + 1) * 8 + 16;
+
+    CUtensorMap map_x, map_w;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cin_total * 2 * D, (cuuint64_t)cin_total * 2 * D * D,
+                                       (cuuint64_t)cin_total * 2 * D * D * D};
+        const cuuint32_t box[5] = {(cuuint32_t)kTileK, (cuuint32_t)D, (cuuint32_t)D, (cuuint32_t)a.dz_box, (cuuint32_t)a.b_box};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        void* base = const_cast<unsigned char*>(static_cast<const unsigned char*>(x_bf16_dev)) + (size_t)cin_off * 2;
+        const CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("mups_conv3d_bn_relu: activation tensor map rejected (CUresult %d)", (int)r); return MUPS_ERR_CUDA; }
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)cin_w, (cuuint64_t)cout, (cuuint64_t)(k * k * k)};
+        const cuuint64_t strides[2] = {(cuuint64_t)cin_w * 2, (cuuint64_t)cin_w * 2 * cout};
+        const cuuint32_t box[3] = {(cuuint32_t)kTileK, (cuuint32_t)n_tile, 1};
+        const cuuint32_t es[3] = {1, 1, 1};
+        const CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16_dev), dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("mups_conv3d_bn_relu: weight tensor map rejected (CUresult %d)", (int)r); return MUPS_ERR_CUDA; }
+    }
+    const long long m_tiles = vox >= kTileM ? (long long)B * (vox / kTileM) : (B + a.b_box - 1) / a.b_box;
+    MUPS_REQUIRE(m_tiles <= 0x7FFFFFFFll, "mups_conv3d_bn_relu: batch too large for one launch");
+    MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_tcgen05_kernel<<<dim3((unsigned)m_tiles, (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
+    MUPS_CHECK_LAUNCH();
+    return MUPS_OK;
+}
+
+}  // extern "C"

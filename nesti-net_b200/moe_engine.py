@@ -1,0 +1,229 @@
+"""The consumer of the MuPS tensor on the B200 tensor cores.
+
+``TensorCoreExperts`` runs the forward pass of the Mixture-of-Experts normal estimator (models/experts_n_est.py:78-108,
+155-314; restated in ``experts_net.ExpertsNormalEstimator``) with every convolution and fully connected layer on the
+hand-written tcgen05 / TMEM / TMA implicit-GEMM kernel of ``csrc/moe_conv.cu`` (``mups_conv3d_bn_relu``): bf16 operands,
+fp32 accumulation in tensor memory, bias + batch norm folded into a per-channel scale / shift and fused with the ReLU in
+the epilogue, every branch of an inception module writing straight into its channel slice of the module's output (the
+concat is free), activations kept NDHWC bf16 on the device between layers.  MuPS goes in as the fp32 tensor the
+statistics kernel wrote and never leaves the GPU.  Pooling (TF 'SAME' average / max pools) runs on torch between the
+kernels: it is a few per cent of the bytes and none of the FLOPs.
+
+Precision: bf16 products, fp32 sums.  The normals stay within a few tenths of a degree of the fp32 network
+(tests/test_gpu.py::test_tensor_core_consumer_against_fp32_network states the measured deviation); that is two orders of
+magnitude below the 5 / 10 degree thresholds of the reference's own metrics (utils/evaluate.py: PGP5, PGP10).
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .experts_net import ExpertsNormalEstimator, _same_pad  # noqa: F401
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _pad8(c):
+    return (int(c) + 7) // 8 * 8
+
+
+def _pad16(c):
+    return (int(c) + 15) // 16 * 16
+
+
+class PackedConv(object):
+    """One conv3d / fully connected layer of the reference with its batch norm (evaluated with the moving statistics,
+    eps 1e-3) and bias folded: weights [k^3][Cout_pad][Cin_pad] bf16 (tap order dz, dy, dx; TF cross-correlation), scale /
+    shift [Cout_pad] fp32."""
+
+    def __init__(self, weight, bias, bn, relu, k, device, in_map=None, cin_pad=None):
+        """weight: [Cout, Cin, k, k, k] (conv) or [Cout, Cin] (linear); in_map: for each real input channel its index in
+        the padded input layout (None: identity)."""
+        w = weight.detach().float().cpu()
+        if w.ndim == 2:
+            w = w[:, :, None, None, None]
+        cout, cin = int(w.shape[0]), int(w.shape[1])
+        self.k, self.relu, self.cout = int(k), bool(relu), cout
+        self.cout_pad = _pad16(cout)
+        self.cin_pad = _pad8(cin) if cin_pad is None else int(cin_pad)
+        wp = torch.zeros((k ** 3, self.cout_pad, self.cin_pad), dtype=torch.float32)
+        idx = torch.arange(cin) if in_map is None else torch.as_tensor(in_map, dtype=torch.long)
+        wp[:, :cout, idx] = w.permute(2, 3, 4, 0, 1).reshape(k ** 3, cout, cin)
+        b = bias.detach().float().cpu() if bias is not None else torch.zeros(cout)
+        if bn is not None:
+            s = bn.weight.detach().float().cpu() / torch.sqrt(bn.running_var.detach().float().cpu() + bn.eps)
+            t = (b - bn.running_mean.detach().float().cpu()) * s + bn.bias.detach().float().cpu()
+        else:
+            s, t = torch.ones(cout), b
+        scale, shift = torch.zeros(self.cout_pad), torch.zeros(self.cout_pad)
+        scale[:cout], shift[:cout] = s, t
+        self.w = wp.to(device=device, dtype=torch.bfloat16).contiguous()
+        self.scale = scale.to(device).contiguous()
+        self.shift = shift.to(device).contiguous()
+
+
+def conv3d_bn_relu(x, cin_off, cin, layer, out=None, cout_off=0, out_f32=None):
+    """x: NDHWC bf16 [B, D, D, D, Ct] (or [B, Ct] for a fully connected layer); reads channels [cin_off, cin_off + cin).
+    Writes layer.cout_pad channels at ``cout_off`` of ``out`` (NDHWC bf16) and / or the fp32 tensor ``out_f32`` [rows, Cout_pad]."""
+    B = int(x.shape[0])
+    D = int(x.shape[1]) if x.ndim == 5 else 1
+    ct = int(x.shape[-1])
+    if out is None and out_f32 is None:
+        out = torch.empty(tuple(x.shape[:-1]) + (layer.cout_pad,), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mups_conv3d_bn_relu(
+            _ptr(x), B, D, ct, int(cin_off), int(cin), _ptr(layer.w), layer.cin_pad, layer.cout_pad, layer.k, _ptr(layer.scale),
+            _ptr(layer.shift), 1 if layer.relu else 0, _ptr(out), int(out.shape[-1]) if out is not None else 0, int(cout_off),
+            _ptr(out_f32), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mups_conv3d_bn_relu")
+    return out if out is not None else out_f32
+
+
+def _ncdhw(x):
+    return x.permute(0, 4, 1, 2, 3)          # a channels_last_3d view of the NDHWC tensor
+
+
+def _avg_pool_same(x, k):
+    """tf.nn.avg_pool3d(padding='SAME', stride 1) on NDHWC bf16: mean over the valid cells of each window (fp32 inside)."""
+    if k == 1:
+        return x
+    a, b = _same_pad(k)
+    v = _ncdhw(x).float()
+    xs = F.avg_pool3d(F.pad(v, (a, b, a, b, a, b)), k, stride=1) * float(k ** 3)
+    ones = torch.ones((1, 1) + tuple(v.shape[2:]), dtype=v.dtype, device=v.device)
+    cnt = F.avg_pool3d(F.pad(ones, (a, b, a, b, a, b)), k, stride=1) * float(k ** 3)
+    return (xs / cnt).permute(0, 2, 3, 4, 1).to(torch.bfloat16).contiguous()
+
+
+def _max_pool_same(x, k, stride):
+    n = int(x.shape[1])
+    out = -(-n // stride)
+    total = max((out - 1) * stride + k - n, 0)
+    a, b = total // 2, total - total // 2
+    v = _ncdhw(x).float()
+    if total:
+        v = F.pad(v, (a, b, a, b, a, b), value=float("-inf"))
+    return F.max_pool3d(v, k, stride=stride).permute(0, 2, 3, 4, 1).to(torch.bfloat16).contiguous()
+
+
+class _PackedInception(object):
+    def __init__(self, m, device, in_map=None, cin_pad=None):
+        self.k0 = m.k0
+        mk = lambda c, im=None, cp=None: PackedConv(c.conv.weight, c.conv.bias, c.bn, True, c.conv.kernel_size[0], device, im, cp)
+        self.one, self.pool = mk(m.one, in_map, cin_pad), mk(m.pool, in_map, cin_pad)
+        self.a, self.b = mk(m.a), mk(m.b)
+        self.nf = self.one.cout_pad
+        self.c_out = 2 * self.nf + self.a.cout_pad + self.b.cout_pad
+        # real-channel positions inside this module's (padded) output, for the next layer's weight packing
+        real = lambda l, off: [off + i for i in range(l.cout)]
+        self.out_map = (real(self.one, 0) + real(self.a, self.nf) + real(self.b, self.nf + self.a.cout_pad)
+                        + real(self.pool, self.nf + self.a.cout_pad + self.b.cout_pad))
+
+    def __call__(self, x, cin_off, cin):
+        out = torch.empty(tuple(x.shape[:-1]) + (self.c_out,), dtype=torch.bfloat16, device=x.device)
+        conv3d_bn_relu(x, cin_off, cin, self.one, out, 0)
+        conv3d_bn_relu(out, 0, self.nf, self.a, out, self.nf)
+        conv3d_bn_relu(out, 0, self.nf, self.b, out, self.nf + self.a.cout_pad)
+        off = self.nf + self.a.cout_pad + self.b.cout_pad
+        if self.k0 == 1:                        # a 1-wide average pool is the identity
+            conv3d_bn_relu(x, cin_off, cin, self.pool, out, off)
+        else:
+            conv3d_bn_relu(_avg_pool_same(x[..., cin_off:cin_off + cin], self.k0), 0, cin, self.pool, out, off)
+        return out
+
+
+class _PackedConvNet(object):
+    def __init__(self, net, device, in_map, cin_pad):
+        self.steps = []
+        it = iter(net.mods)
+        cur_map, cur_pad = in_map, cin_pad
+        for step in net.plan:
+            if step is None:
+                inc = _PackedInception(next(it), device, cur_map, cur_pad)
+                self.steps.append(inc)
+                cur_map, cur_pad = inc.out_map, inc.c_out
+            else:
+                self.steps.append(step)
+        self.out_map, self.out_pad = cur_map, cur_pad
+
+    def __call__(self, x, cin_off, cin):
+        for step in self.steps:
+            if isinstance(step, _PackedInception):
+                x = step(x, cin_off, cin)
+                cin_off, cin = 0, int(x.shape[-1])
+            else:
+                x = _max_pool_same(x, step[1], step[2])
+        if x.shape[1] != 1:
+            raise ValueError("only the 8^3 networks of the reference (which end at a 1^3 volume) are packed for the tensor cores")
+        return x.reshape(x.shape[0], -1)       # TF flattens channels-last [B, d, h, w, C]
+
+
+class TensorCoreExperts(object):
+    """``ExpertsNormalEstimator`` packed for the tcgen05 kernel.  ``predict(mups)`` takes the fp32 MuPS tensor
+    [B, res, res, res, 20 S] on the GPU and returns (normal of the most probable expert [B, 3], expert [B],
+    probabilities [B, n_experts]) like ``ExpertsNormalEstimator.predict``."""
+
+    def __init__(self, model, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("TensorCoreExperts needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        model = model.eval()
+        self.expert_dict = model.expert_dict
+        first = model.gate_conv.mods[0].one.conv
+        self.n_rads = int(first.in_channels) // 20
+        S = self.n_rads
+        scale_map = lambda scales: [32 * i + c for i in range(len(scales)) for c in range(20)]      # 20 real channels per 32-wide scale slot
+        self.gate = _PackedConvNet(model.gate_conv, self.device, scale_map(range(S)), 32 * S)
+        self.gate_fc = self._pack_fc(model.gate_fc, self.gate)
+        self.experts = []
+        for i, (conv, fc) in enumerate(zip(model.expert_conv, model.expert_fc)):
+            scales = self.expert_dict[i]
+            net = _PackedConvNet(conv, self.device, scale_map(scales), 32 * len(scales))
+            self.experts.append((int(np.min(scales)) * 32, 32 * len(scales), net, self._pack_fc(fc, net)))
+        self.n_experts = len(self.experts)
+
+    def _pack_fc(self, seq, net):
+        layers, in_map, pad = [], net.out_map, net.out_pad
+        for fc in seq:
+            l = PackedConv(fc.lin.weight, fc.lin.bias, fc.bn, fc.relu, 1, self.device, in_map, pad)
+            layers.append(l)
+            in_map, pad = None, l.cout_pad
+        return layers
+
+    def _run_fc(self, layers, x):
+        for l in layers[:-1]:
+            x = conv3d_bn_relu(x, 0, int(x.shape[-1]), l)
+        last = layers[-1]
+        out = torch.empty((x.shape[0], last.cout_pad), dtype=torch.float32, device=x.device)
+        conv3d_bn_relu(x, 0, int(x.shape[-1]), last, None, 0, out)
+        return out[:, :last.cout]
+
+    def pack_input(self, mups):
+        """fp32 MuPS [B, res, res, res, 20 S] -> bf16 [B, res, res, res, 32 S] (every scale padded to 32 channels)."""
+        B, res = int(mups.shape[0]), int(mups.shape[1])
+        S = self.n_rads
+        x = torch.empty((B, res, res, res, 32 * S), dtype=torch.bfloat16, device=mups.device)
+        with torch.cuda.device(mups.device):
+            _lib.check(_lib.load().mups_moe_pack_input(_ptr(mups), B * res ** 3, S, _ptr(x),
+                                                       ctypes.c_void_p(torch.cuda.current_stream(mups.device).cuda_stream)),
+                       "mups_moe_pack_input")
+        return x
+
+    @torch.no_grad()
+    def forward(self, mups):
+        """(experts_prob [n_experts, B], n_est [n_experts, B, 3]) like ExpertsNormalEstimator.forward."""
+        mups = mups.to(self.device, torch.float32).contiguous()
+        x = self.pack_input(mups)
+        logits = self._run_fc(self.gate_fc, self.gate(x, 0, int(x.shape[-1])))
+        prob = F.softmax(logits, dim=1).transpose(0, 1)
+        normals = [self._run_fc(fc, net(x, off, width)) for off, width, net, fc in self.experts]
+        return prob, torch.stack(normals)
+
+    @torch.no_grad()
+    def predict(self, mups):
+        prob, n_est = self.forward(mups)
+        expert = prob.argmax(dim=0)
+        return n_est[expert, torch.arange(n_est.shape[1], device=n_est.device)], expert, prob.transpose(0, 1)

@@ -902,6 +902,96 @@ def test_inference_driver(tmp_path):
         assert mb.evaluate.evaluate_shape(normals, ref_n.numpy())["pgp5"] > 0.99
 
 
+def _conv_reference(x, cin_off, cin, w, scale, shift, relu, k):
+    """fp32 reference of mups_conv3d_bn_relu on the bf16-rounded operands: TF 'SAME' cross-correlation, scale / shift, ReLU."""
+    import torch.nn.functional as F
+    xs = x[..., cin_off:cin_off + cin].float()
+    if xs.ndim == 2:
+        xs = xs[:, None, None, None, :]
+    v = xs.permute(0, 4, 1, 2, 3)
+    a, b = (k - 1) // 2, (k - 1) - (k - 1) // 2
+    kk = w.float().reshape(k, k, k, w.shape[1], w.shape[2]).permute(3, 4, 0, 1, 2)[:, :cin]      # [Cout, Cin, kd, kh, kw]
+    y = F.conv3d(F.pad(v, (a, b, a, b, a, b)), kk)
+    y = y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 4, 1)
+
+
+@pytest.mark.parametrize("D,k,ct,cin_off,cin,cout,B", [
+    (8, 1, 128, 0, 128, 128, 3), (8, 3, 128, 0, 128, 64, 2), (8, 5, 64, 0, 64, 64, 2), (8, 3, 128, 32, 32, 32, 2),
+    (8, 5, 256, 0, 256, 128, 1), (4, 2, 768, 0, 768, 256, 5), (4, 4, 512, 0, 512, 256, 3), (2, 2, 512, 0, 512, 256, 37),
+    (2, 1, 1536, 0, 1536, 512, 20), (1, 1, 1536, 0, 1536, 1024, 300), (1, 1, 128, 0, 128, 16, 130), (8, 3, 96, 0, 96, 16, 1)])
+def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
+    """mups_conv3d_bn_relu (tcgen05 / TMEM / TMA implicit GEMM, csrc/moe_conv.cu) against torch conv3d in fp32 on the same
+    bf16-rounded operands: every volume edge and kernel edge of the reference's networks, 'SAME' padding for even kernels,
+    channel-slice inputs and outputs, batch tails of the 128-row tile, the fully connected layers (D = 1), fp32 output."""
+    from nesti_net_b200 import moe_engine as me
+    torch.manual_seed(D * 100 + k * 10 + cout)
+    dev = torch.device("cuda", 0)
+    shape = (B, D, D, D, ct) if D > 1 else (B, ct)
+    x = torch.randn(shape, device=dev).to(torch.bfloat16)
+    layer = me.PackedConv.__new__(me.PackedConv)
+    layer.k, layer.relu, layer.cout, layer.cout_pad, layer.cin_pad = k, True, cout, cout, cin
+    layer.w = (torch.randn((k ** 3, cout, cin), device=dev) / np.sqrt(cin * k ** 3)).to(torch.bfloat16).contiguous()
+    layer.scale = torch.rand(cout, device=dev) + 0.5
+    layer.shift = torch.randn(cout, device=dev) * 0.1
+    out = torch.full(shape[:-1] + (cout + 16,), 7.0, dtype=torch.bfloat16, device=dev)      # the kernel writes a channel slice
+    f32 = torch.empty((x.numel() // ct, cout), dtype=torch.float32, device=dev)
+    me.conv3d_bn_relu(x, cin_off, cin, layer, out, 8, f32)
+    torch.cuda.synchronize()
+    ref = _conv_reference(x, cin_off, cin, layer.w, layer.scale, layer.shift, True, k).reshape(-1, cout)
+    err = (f32 - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), "fp32 output: max err %.3g" % err
+    got = out.reshape(-1, cout + 16)
+    assert torch.all(got[:, :8] == 7.0) and torch.all(got[:, 8 + cout:] == 7.0), "wrote outside its channel slice"
+    assert torch.equal(got[:, 8:8 + cout], f32.to(torch.bfloat16)), "bf16 output is not the rounded fp32 output"
+
+
+def test_tensor_core_consumer_against_fp32_network():
+    """The Mixture-of-Experts forward on the tcgen05 kernels (moe_engine.TensorCoreExperts) against the fp32 PyTorch
+    network (experts_net.ExpertsNormalEstimator, TF32 off) on GPU MuPS of a real cloud, batch norm statistics randomised
+    so that the folding is exercised: same expert for (almost) every query, gate probabilities close, normals within a
+    fraction of a degree -- bf16 products with fp32 accumulation; the deviation is printed."""
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg
+    from nesti_net_b200.moe_engine import TensorCoreExperts
+    pts = orc.synthetic_cloud(30000, cloud_id=9, noise=0.001)
+    radius, P = [0.01, 0.03, 0.05, 0.07], 512
+    w, mu, sg = grid_gmm(8, 0.0156)
+    q = np.random.RandomState(8).choice(30000, 200, replace=False)
+    index = mb.PointIndex(pts, cell_frac=max(radius))
+    mups = mb.mups_features(index, mb.gmm_handle(w, mu, sg), q, index.absolute_radii(radius), P, seed=SEED)
+    torch.manual_seed(1234)
+    net = ExpertsNormalEstimator(n_rads=4, n_gaussians=512, n_experts=7).eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, (torch.nn.BatchNorm3d, torch.nn.BatchNorm1d)):
+                m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.6, 1.5); m.weight.uniform_(0.7, 1.3); m.bias.normal_(0, 0.05)
+            if isinstance(m, (torch.nn.Conv3d, torch.nn.Linear)):
+                m.bias.normal_(0, 0.02)
+    net = net.cuda()
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            prob_ref, n_ref = net(mups)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    tc = TensorCoreExperts(net)
+    prob, n_est = tc.forward(mups)
+    torch.cuda.synchronize()
+    assert tuple(prob.shape) == tuple(prob_ref.shape) and tuple(n_est.shape) == tuple(n_ref.shape)
+    assert torch.isfinite(prob).all() and torch.isfinite(n_est).all()
+    same = prob.argmax(0) == prob_ref.argmax(0)
+    rms = angular_rms_deg(n_est.reshape(-1, 3), n_ref.reshape(-1, 3))
+    dprob = float((prob - prob_ref).abs().max())
+    print("tensor-core consumer vs fp32 network: angular RMS %.3g deg over all experts, same expert %d/%d, max |dprob| %.3g"
+          % (rms, int(same.sum()), len(q), dprob))
+    assert rms < 1.0 and int(same.sum()) >= int(0.9 * len(q)) and dprob < 0.05
+    sel, expert, probs = tc.predict(mups)
+    assert tuple(sel.shape) == (len(q), 3) and tuple(probs.shape) == (len(q), 7) and torch.equal(expert, prob.argmax(0))
+
+
 def test_downstream_moe_normals():
     """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
     models/experts_n_est.py, fp32) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4 angular
