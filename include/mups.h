@@ -162,6 +162,11 @@ int mups_features(const mups_index* index, const mups_gmm* gmm, const int64_t* q
 /* MuPS fp32 [rows, 20 S] (rows = B * res^3, as mups_3dmfv wrote it) -> bf16 [rows, 32 S]: each scale's 20 channels padded
  * to 32, the activation layout of the kernels below (channel slices of the single-scale experts 16-byte aligned). */
 int mups_moe_pack_input(const float* mups_dev, int64_t rows, int S, void* out_bf16_dev, mups_stream stream);
+/* tf_util.avg_pool3d (utils/tf_util.py:432-455; window k, stride 1, 'SAME': mean over the valid cells, is_max = 0) and
+ * tf_util.max_pool3d (:406-430; window 2, stride 2, is_max = 1) on channels [c_off, c_off + c) of x_bf16_dev NDHWC bf16
+ * [B, D, D, D, c_total]; y_bf16_dev: [B, D', D', D', c] contiguous (D' = D, or D / 2 for the max pool). */
+int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, int is_max, void* y_bf16_dev,
+                mups_stream stream);
 /* tf_util.conv3d (utils/tf_util.py:254-311: stride 1, 'SAME', bias, batch norm, ReLU) and tf_util.fully_connected
  * (:314-351; D = 1, k = 1) as one tcgen05 implicit GEMM:
  *   y[b,z,y,x,co] = act(scale[co] * sum_{dz,dy,dx,ci} x[b, z+dz-p, y+dy-p, x+dx-p, cin_off+ci] * w[(dz*k+dy)*k+dx][co][ci] + shift[co])

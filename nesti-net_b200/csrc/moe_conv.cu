@@ -234,6 +234,56 @@ __global__ void __launch_bounds__(256) pack_mups_bf16_kernel(const float* __rest
     }
 }
 
+// tf.nn.avg_pool3d(ksize k, stride 1, 'SAME') on NDHWC bf16: mean over the VALID cells of each window (the padding does not
+// count, utils/tf_util.py:432-455), fp32 inside; and tf.nn.max_pool3d(2, stride 2) (:406-430).  One thread per (output voxel,
+// 8-channel chunk): 16-byte loads / stores, memory bound, the window re-reads hit L1 / L2.
+__global__ void __launch_bounds__(256) pool3d_kernel(const __nv_bfloat16* __restrict__ x, long long B, int D, int ct, int c_off, int c,
+                                                     int k, int is_max, __nv_bfloat16* __restrict__ y) {
+    const int chunks = c >> 3;
+    const int Do = is_max ? D / 2 : D;
+    const long long n = B * Do * Do * Do * chunks;
+    const int pl = (k - 1) / 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        long long v = i / chunks;
+        const int xo = (int)(v % Do), yo = (int)((v / Do) % Do), zo = (int)((v / ((long long)Do * Do)) % Do);
+        const long long b = v / ((long long)Do * Do * Do);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = is_max ? -INFINITY : 0.f;
+        int cnt = 0;
+        const int z0 = is_max ? 2 * zo : zo - pl, y0 = is_max ? 2 * yo : yo - pl, x0 = is_max ? 2 * xo : xo - pl;
+        const int kk = is_max ? 2 : k;
+        for (int dz = 0; dz < kk; ++dz) {
+            const int z = z0 + dz;
+            if (z < 0 || z >= D) continue;
+            for (int dy = 0; dy < kk; ++dy) {
+                const int yy = y0 + dy;
+                if (yy < 0 || yy >= D) continue;
+                for (int dx = 0; dx < kk; ++dx) {
+                    const int xx = x0 + dx;
+                    if (xx < 0 || xx >= D) continue;
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (((b * D + z) * D + yy) * D + xx) * (long long)ct + c_off) + ch);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = __bfloat1622float2(h[j]);
+                        if (is_max) { acc[2 * j] = fmaxf(acc[2 * j], f.x); acc[2 * j + 1] = fmaxf(acc[2 * j + 1], f.y); }
+                        else { acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+                    }
+                    ++cnt;
+                }
+            }
+        }
+        const float inv = is_max ? 1.f : 1.f / (float)cnt;
+        uint4 out;
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
+        reinterpret_cast<uint4*>(y + v * (long long)c)[ch] = out;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -263,6 +313,21 @@ int mups_moe_pack_input(const float* mups_dev, int64_t rows, int S, void* out_bf
     const long long n = (long long)rows * S * 32;
     const int grid = (int)((n + 255) / 256 < 16 * kNumSMs ? (n + 255) / 256 : 16 * kNumSMs);
     pack_mups_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(mups_dev, rows, S, static_cast<__nv_bfloat16*>(out_bf16_dev));
+    MUPS_CHECK_LAUNCH();
+    return MUPS_OK;
+}
+
+int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, int is_max, void* y_bf16_dev,
+                mups_stream stream) {
+    MUPS_REQUIRE(x_bf16_dev && y_bf16_dev, "mups_pool3d: NULL buffer");
+    MUPS_REQUIRE(B >= 1 && (D == 2 || D == 4 || D == 8), "mups_pool3d: B=%lld, volume edge %d", (long long)B, D);
+    MUPS_REQUIRE(c >= 8 && c % 8 == 0 && c_total % 8 == 0 && c_off % 8 == 0 && c_off + c <= c_total, "mups_pool3d: channels (%d of %d at %d) must be multiples of 8", c, c_total, c_off);
+    MUPS_REQUIRE(is_max ? k == 2 : (k >= 1 && k <= 5), "mups_pool3d: window %d", k);
+    const int Do = is_max ? D / 2 : D;
+    const long long n = (long long)B * Do * Do * Do * (c / 8);
+    const int grid = (int)((n + 255) / 256 < 32 * kNumSMs ? (n + 255) / 256 : 32 * kNumSMs);
+    pool3d_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16_dev), B, D, c_total, c_off, c, k,
+                                                                         is_max, static_cast<__nv_bfloat16*>(y_bf16_dev));
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;
 }

@@ -6,8 +6,8 @@ hand-written tcgen05 / TMEM / TMA implicit-GEMM kernel of ``csrc/moe_conv.cu`` (
 fp32 accumulation in tensor memory, bias + batch norm folded into a per-channel scale / shift and fused with the ReLU in
 the epilogue, every branch of an inception module writing straight into its channel slice of the module's output (the
 concat is free), activations kept NDHWC bf16 on the device between layers.  MuPS goes in as the fp32 tensor the
-statistics kernel wrote and never leaves the GPU.  Pooling (TF 'SAME' average / max pools) runs on torch between the
-kernels: it is a few per cent of the bytes and none of the FLOPs.
+statistics kernel wrote and never leaves the GPU.  The TF 'SAME' average pools and the 2/2 max pools are one small bf16
+NDHWC kernel (``mups_pool3d``); torch is left with the softmax over seven gate outputs.
 
 Precision: bf16 products, fp32 sums.  The normals stay within a few tenths of a degree of the fp32 network
 (tests/test_gpu.py::test_tensor_core_consumer_against_fp32_network states the measured deviation); that is two orders of
@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .experts_net import ExpertsNormalEstimator, _same_pad  # noqa: F401
+from .experts_net import ExpertsNormalEstimator  # noqa: F401
 
 
 def _ptr(t):
@@ -82,31 +82,16 @@ def conv3d_bn_relu(x, cin_off, cin, layer, out=None, cout_off=0, out_f32=None):
     return out if out is not None else out_f32
 
 
-def _ncdhw(x):
-    return x.permute(0, 4, 1, 2, 3)          # a channels_last_3d view of the NDHWC tensor
-
-
-def _avg_pool_same(x, k):
-    """tf.nn.avg_pool3d(padding='SAME', stride 1) on NDHWC bf16: mean over the valid cells of each window (fp32 inside)."""
-    if k == 1:
-        return x
-    a, b = _same_pad(k)
-    v = _ncdhw(x).float()
-    xs = F.avg_pool3d(F.pad(v, (a, b, a, b, a, b)), k, stride=1) * float(k ** 3)
-    ones = torch.ones((1, 1) + tuple(v.shape[2:]), dtype=v.dtype, device=v.device)
-    cnt = F.avg_pool3d(F.pad(ones, (a, b, a, b, a, b)), k, stride=1) * float(k ** 3)
-    return (xs / cnt).permute(0, 2, 3, 4, 1).to(torch.bfloat16).contiguous()
-
-
-def _max_pool_same(x, k, stride):
-    n = int(x.shape[1])
-    out = -(-n // stride)
-    total = max((out - 1) * stride + k - n, 0)
-    a, b = total // 2, total - total // 2
-    v = _ncdhw(x).float()
-    if total:
-        v = F.pad(v, (a, b, a, b, a, b), value=float("-inf"))
-    return F.max_pool3d(v, k, stride=stride).permute(0, 2, 3, 4, 1).to(torch.bfloat16).contiguous()
+def pool3d(x, c_off, c, k, is_max):
+    """tf_util.avg_pool3d (window k, stride 1, 'SAME': mean over the valid cells) or max_pool3d (2, stride 2) on channels
+    [c_off, c_off + c) of the NDHWC bf16 tensor x (mups_pool3d) -> contiguous NDHWC bf16."""
+    B, D = int(x.shape[0]), int(x.shape[1])
+    Do = D // 2 if is_max else D
+    y = torch.empty((B, Do, Do, Do, int(c)), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mups_pool3d(_ptr(x), B, D, int(x.shape[-1]), int(c_off), int(c), int(k), 1 if is_max else 0, _ptr(y),
+                                           ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mups_pool3d")
+    return y
 
 
 class _PackedInception(object):
@@ -131,7 +116,7 @@ class _PackedInception(object):
         if self.k0 == 1:                        # a 1-wide average pool is the identity
             conv3d_bn_relu(x, cin_off, cin, self.pool, out, off)
         else:
-            conv3d_bn_relu(_avg_pool_same(x[..., cin_off:cin_off + cin], self.k0), 0, cin, self.pool, out, off)
+            conv3d_bn_relu(pool3d(x, cin_off, cin, self.k0, False), 0, cin, self.pool, out, off)
         return out
 
 
@@ -155,7 +140,9 @@ class _PackedConvNet(object):
                 x = step(x, cin_off, cin)
                 cin_off, cin = 0, int(x.shape[-1])
             else:
-                x = _max_pool_same(x, step[1], step[2])
+                if (step[1], step[2]) != (2, 2) or x.shape[1] % 2:
+                    raise ValueError("only the 2-wide, stride-2 max pools of the reference's 8^3 networks are packed")
+                x = pool3d(x, 0, int(x.shape[-1]), 2, True)
         if x.shape[1] != 1:
             raise ValueError("only the 8^3 networks of the reference (which end at a 1^3 volume) are packed for the tensor cores")
         return x.reshape(x.shape[0], -1)       # TF flattens channels-last [B, d, h, w, C]

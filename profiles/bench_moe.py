@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""SURVEY.md 8(f) rank 1, the consumer of MuPS: forward throughput of the (random-init) Mixture-of-Experts on one B200
-in strict fp32, TF32 and bf16 (torch / cuDNN library kernels, channels-last-3d), and what each precision does to the
-normals relative to strict fp32 on the host (the checker of the fourth parity gate).  MuPS inputs come from the GPU
+"""SURVEY.md 8(f) rank 1, the consumer of MuPS: forward throughput of the (random-init) Mixture-of-Experts on one B200 --
+the hand-written tcgen05 engine (moe_engine.TensorCoreExperts: bf16 products, fp32 accumulation in tensor memory) against
+torch / cuDNN library kernels in strict fp32, TF32 and bf16 autocast -- and what each does to the normals relative to strict
+fp32 on the host (the checker of the fourth parity gate).  MuPS inputs come from the GPU
 path on a synthetic cloud.  One JSON line per mode."""
 import json
 import os
@@ -15,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import nesti_net_b200 as mb  # noqa: E402
 from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg  # noqa: E402
-from oracle import mups_oracle as orc  # noqa: E402   (synthetic cloud only)
+from nesti_net_b200.moe_engine import TensorCoreExperts  # noqa: E402
+from nesti_net_b200.synthetic import synthetic_cloud  # noqa: E402
 
 SEED = 3627473
 RADIUS = [0.01, 0.03, 0.05, 0.07]
@@ -24,7 +26,7 @@ RADIUS = [0.01, 0.03, 0.05, 0.07]
 def main():
     B = int(os.environ.get("B", 256))
     n_ref = 32
-    pts = orc.synthetic_cloud(100000, cloud_id=0, noise=0.001)
+    pts = synthetic_cloud(100000, cloud_id=0, noise=0.001)
     g = mb.get_3d_grid_gmm([8, 8, 8], 0.0156)
     gmm = mb.gmm_handle(g.weights_, g.means_, np.sqrt(g.covariances_))
     index = mb.PointIndex(pts, cell_frac=max(RADIUS))
@@ -79,6 +81,29 @@ def main():
                               "normals_rms_deg_vs_host_fp32": rms, "same_expert": "%d/%d" % (int(same.sum()), n_ref)}), flush=True)
         except Exception as e:      # a mode the library cannot run is a finding, not a failure of the script
             print(json.dumps({"mode": name, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}), flush=True)
+
+
+    # ---- the hand-written tensor-core engine --------------------------------------------------------------------
+    tc = TensorCoreExperts(net)
+    for bsz in sorted({B, int(os.environ.get("B_TC", 1024))}):
+        qq = np.random.RandomState(1).choice(100000, bsz, replace=False)
+        x = mb.mups_features(index, gmm, qq, index.absolute_radii(RADIUS), 512, seed=SEED)
+        tc.predict(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            out = tc.predict(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        n_s, e_s, _ = tc.predict(mups[:n_ref])
+        same = (e_s.cpu() == ref_e)
+        rms = float(angular_rms_deg(n_s.float().cpu()[same], ref_n[same])) if bool(same.any()) else None
+        flops = 6.0e10 * bsz
+        print(json.dumps({"mode": "tcgen05 engine (bf16 x bf16 -> fp32 in TMEM)", "batch": bsz, "ms_per_batch": round(ms, 2),
+                          "queries_per_s": round(bsz / ms * 1e3, 1), "approx_TFLOPs": round(flops / ms / 1e9, 1),
+                          "normals_rms_deg_vs_host_fp32": rms, "same_expert": "%d/%d" % (int(same.sum()), n_ref)}), flush=True)
 
 
 if __name__ == "__main__":

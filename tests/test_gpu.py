@@ -948,6 +948,21 @@ def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     assert torch.equal(got[:, 8:8 + cout], f32.to(torch.bfloat16)), "bf16 output is not the rounded fp32 output"
 
 
+@pytest.mark.parametrize("D,k,is_max", [(8, 3, False), (4, 2, False), (8, 2, False), (8, 2, True), (4, 2, True), (2, 2, True)])
+def test_pool3d_against_tf_semantics(D, k, is_max):
+    """mups_pool3d against experts_net.avg_pool_same / max_pool_same (TF 'SAME': the average counts only valid cells) on a
+    channel slice of a bf16 NDHWC tensor."""
+    from nesti_net_b200 import moe_engine as me
+    from nesti_net_b200.experts_net import avg_pool_same, max_pool_same
+    torch.manual_seed(D + k)
+    x = torch.randn((5, D, D, D, 96), device="cuda").to(torch.bfloat16)
+    got = me.pool3d(x, 16, 64, k, is_max)
+    v = x[..., 16:80].float().permute(0, 4, 1, 2, 3)
+    ref = (max_pool_same(v, 2, 2) if is_max else avg_pool_same(v, k)).permute(0, 2, 3, 4, 1)
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert torch.equal(got, ref.to(torch.bfloat16)) if is_max else (got.float() - ref).abs().max().item() < 2e-2
+
+
 def test_tensor_core_consumer_against_fp32_network():
     """The Mixture-of-Experts forward on the tcgen05 kernels (moe_engine.TensorCoreExperts) against the fp32 PyTorch
     network (experts_net.ExpertsNormalEstimator, TF32 off) on GPU MuPS of a real cloud, batch norm statistics randomised
