@@ -721,6 +721,36 @@ def run_clouds(args, cfg):
                                   "checksum_finite": bool(np.isfinite(checksum)),
                                   "api": "MuPSPipeline.features_to_consumer (host cloud in, MuPS reduced on the GPU)"}
 
+    # ---- the reference's user-visible path (test_n_est_w_experts.py:129-197): host cloud in -> MuPS -> Mixture-of-Experts ->
+    # normals out, with the consumer on the tensor cores (moe_engine.TensorCoreExperts: hand-written tcgen05 conv3d, random-init
+    # network) fed chunk by chunk through MuPSPipeline.features_to_consumer, so MuPS never leaves the device
+    if "e2e" not in skip and "normals" not in skip and RES == 8 and rank == 0:
+        from nesti_net_b200.experts_net import ExpertsNormalEstimator
+        from nesti_net_b200.moe_engine import TensorCoreExperts
+        torch.manual_seed(1234)
+        tc = TensorCoreExperts(ExpertsNormalEstimator(n_rads=S, n_gaussians=G, n_experts=7).eval().to(dev))
+        nq_n = int(os.environ.get("MUPS_BENCH_NORMALS_QUERIES", "16384"))
+        pipe_n = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=1024)
+        normals_host = torch.empty((nq_n, 3), dtype=torch.float32).pin_memory()
+        qn_host = (torch.arange(nq_n, dtype=torch.int64) * (N_POINTS // nq_n)).pin_memory()
+
+        def to_normals(lo_, hi_, rows_):
+            nrm, _, _ = tc.predict(rows_.view(hi_ - lo_, RES, RES, RES, 20 * S))
+            normals_host[lo_:hi_].copy_(nrm, non_blocking=True)
+        pipe_n.features_to_consumer(hosts[0], qn_host[:2048], to_normals)
+        torch.cuda.synchronize()
+        pipe_n.h2d_bytes = 0
+        w0 = time.perf_counter()
+        n_n = pipe_n.features_to_consumer(hosts[1 % len(hosts)], qn_host, to_normals)
+        torch.cuda.synchronize()
+        nt = time.perf_counter() - w0
+        e2e["normals"] = {"value": n_n / nt, "unit": UNIT, "queries": n_n, "h2d_bytes_per_step": pipe_n.h2d_bytes,
+                          "d2h_bytes_per_step": n_n * 12, "chunk_queries": pipe_n.chunk, "finite": bool(torch.isfinite(normals_host).all()),
+                          "api": "host cloud in -> MuPSPipeline.features_to_consumer -> moe_engine.TensorCoreExperts.predict (tcgen05 conv3d, "
+                                 "bf16 x bf16 -> fp32) -> normals to pinned host memory; random-init 7-expert network, one GPU",
+                          "cudnn_strict_fp32_queries_per_s": 773, "cudnn_source": "profiles/r02_moe.jsonl"}
+        del tc, pipe_n
+
     cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                     "sample": "measured at N=1 only (see the N=1 line / --impl reference)"}
     if rank == 0 and n_gpus == 1:

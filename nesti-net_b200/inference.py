@@ -21,7 +21,8 @@ def estimate_normals(indir, dataset_name, outdir, model, gmm, patch_radius, poin
     """Returns {shape name: (normals [n,3], experts [n], experts_probs [n, n_experts])} and, when
     `write`, saves them with np.savetxt exactly as test_n_est_w_experts.py:185-191 does.
 
-    model: nesti_net_b200.experts_net.ExpertsNormalEstimator (any device; MuPS is moved to it)
+    model: nesti_net_b200.experts_net.ExpertsNormalEstimator (any device; MuPS is moved to it), or a
+           nesti_net_b200.moe_engine.TensorCoreExperts (the same network packed for the tcgen05 kernels: MuPS stays on the GPU)
     gmm:   GridGMM-like (weights_, means_, covariances_)"""
     loader, dataset = get_data_loader(
         dataset_name=dataset_name, batchSize=batch_size, indir=indir, patch_radius=patch_radius,
@@ -29,10 +30,12 @@ def estimate_normals(indir, dataset_name, outdir, model, gmm, patch_radius, poin
         use_pca=False, patch_center='point', point_tuple=1, cache_capacity=100, patch_sample_order='full',
         workers=0, dataset_type='test', sparse_patches=sparse_patches)
     handle = _m.gmm_handle(gmm.weights_, gmm.means_, np.sqrt(gmm.covariances_))
-    model_device = next(model.parameters()).device
-    model.eval()
+    packed = not hasattr(model, "parameters")
+    model_device = model.device if packed else next(model.parameters()).device
+    if not packed:
+        model.eval()
     cudnn_benchmark = torch.backends.cudnn.benchmark
-    if model_device.type == "cuda":
+    if model_device.type == "cuda" and not packed:
         torch.backends.cudnn.benchmark = True      # the 8^3 conv3d stack is 2-3x faster with cuDNN's tuned algorithms (restored below)
     n_rads = len(patch_radius)
     normals, experts, probs = [], [], []
