@@ -75,7 +75,8 @@ int64_t mups_launch_count(void);
  * refinement path, which otherwise needs > ~500k neighbours in one ball).
  * "fuse_candidates" (default 12288): candidate points in a ball's first cell batch above which the
  * first scan also builds the subsample's key histograms (dense balls; results never depend on it).
- * "stats_variant" (0 = automatic; 1 round-1 loop and staging, 2 all-scalar loop, 8 no cluster at 16^3):
+ * "stats_variant" (0 = automatic; 1 round-1 loop and staging, 2 all-scalar loop, 3 two (query, scale) items per CTA with the
+ * patches delivered by cp.async.bulk + mbarrier, 8 no cluster at 16^3):
  * force a statistics-kernel variant (benchmarking only).
  * "query_kernel" (0 = automatic: hierarchical for indices with >= 6 Morton bits per axis, i.e. fine grids; 1 = flat
  * cell scan; 2 = hierarchical), "query_order" (0 = automatic; 1 = CTAs in caller order; 2 = CTAs in Morton order of the

@@ -386,9 +386,23 @@ __device__ __forceinline__ float sqrt_approx(float x) {   // max relative error 
 // serially -- no shuffle reductions, ~1/3 fewer instructions and much shorter dependency chains than one lane per
 // (pair, axis, lattice index); table rows are padded to RES + 1 entries so that these strided writers stay
 // bank-conflict free (the readers touch one row per step and do not care).
+// ---- bulk-copy (TMA, 1-D) helpers of the two-items-per-CTA variant -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_wait(uint32_t bar, uint32_t parity) {          // bounded: a stuck copy traps instead of hanging
+    for (uint32_t i = 0; i < (1u << 22); ++i) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// One (query, scale) item of the lattice kernel.  coords: shared-memory buffer of the patch; wait_bar != 0: the patch is
+// being delivered by a bulk copy that completes on that mbarrier (two-items-per-CTA variant), else it is loaded here.
 template <int MODE, int LOG_RES, int CL, int STG>
-__global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_kernel(const StatsArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void stats_separable_item(const StatsArgs& a, unsigned char* smem_raw, const int item, float* coords,
+                                                     const uint32_t wait_bar) {
     constexpr int TILE = CL > 1 ? kSepClusterTilePoints : kSepTilePoints;
     constexpr int NT = kSepThreads, TPP = TILE / 2;
     constexpr bool PAIRSUM = MODE != 0;
@@ -409,14 +423,12 @@ __global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_ke
     float* inv_norm = red + (NT / 32) * 20;                    // [20] (+12 pad)
     float* axis_par = inv_norm + 20;                           // [3][4]: 1/sigma, guard lo, guard hi
     float* cl_sq = inv_norm + 32;                              // [CL][20] per-CTA sums of squares (cluster exchange)
-    float* coords = cl_sq + (CL > 1 ? CL * 20 : 0);            // [3*P] the patch, staged once (coalesced)
     __shared__ int s_fallback;
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned crank = CL > 1 ? cluster.block_rank() : 0u;
 
     const int tid = threadIdx.x;
     const int S = a.S, P = a.P;
-    const int item = CL > 1 ? blockIdx.x / CL : blockIdx.x;
     const int64_t b = item / S;
     const int s = item % S;
     const bool masked = (a.flags & MUPS_FLAG_MASKED) != 0;
@@ -425,7 +437,9 @@ __global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_ke
     const int m = masked ? min(n_eff + 1, P) : P;       // slots with r > n_eff are masked (tf_util.py:696)
     const bool any_masked = m < P;
     for (int i = tid; i < 3 * 64; i += NT) lat[i] = __ldg(a.axis_mu + i);
-    if (a.g_sorted) {
+    if (wait_bar) {
+        bulk_wait(wait_bar, 0);                    // the patch was requested before the previous item's main loop
+    } else if (a.g_sorted) {
         const float4 cq = gather_centre(a, b);
         for (int t = tid; t < m; t += NT) {
             const float3 v = gathered_point(a, b, s, t, cq);
@@ -756,6 +770,52 @@ __global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_ke
     }
 }
 
+template <int MODE, int LOG_RES, int CL, int STG>
+__global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_kernel(const StatsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE = CL > 1 ? kSepClusterTilePoints : kSepTilePoints;
+    constexpr int PITCH = STG ? (1 << LOG_RES) + 1 : (1 << LOG_RES);
+    float* coords = reinterpret_cast<float*>(smem_raw + (size_t)(TILE / 2) * 3 * PITCH * (sizeof(float4) + sizeof(float2))) +
+                    3 * 64 + (kSepThreads / 32) * 20 + 32 + (CL > 1 ? CL * 20 : 0);
+    stats_separable_item<MODE, LOG_RES, CL, STG>(a, smem_raw, CL > 1 ? blockIdx.x / CL : blockIdx.x, coords, 0u);
+}
+
+// Variant 3 (mups_set_option "stats_variant"): TWO (query, scale) items per CTA; both patches are requested at kernel start
+// with cp.async.bulk (TMA, 1-D) completing on an mbarrier each, so the second item's patch arrives under the first item's
+// main loop and the lattice / per-axis parameters are staged once.  Patch tensor path only (the K6 gather cannot be a bulk copy).
+template <int MODE, int LOG_RES>
+__global__ void __launch_bounds__(kSepThreads, kSepMinBlocks) stats_separable_pair_kernel(const StatsArgs a, const int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PITCH = (1 << LOG_RES) + 1;
+    float* coords = reinterpret_cast<float*>(smem_raw + (size_t)(kSepTilePoints / 2) * 3 * PITCH * (sizeof(float4) + sizeof(float2))) +
+                    3 * 64 + (kSepThreads / 32) * 20 + 32;
+    __shared__ __align__(8) unsigned long long bars[2];
+    const int first = 2 * blockIdx.x;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 2; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr32(bars + k)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int k = 0; k < 2 && first + k < n_items; ++k) {
+            const int item = first + k;
+            const int64_t b = item / a.S;
+            const int sc = item % a.S;
+            int n_eff = (a.flags & MUPS_FLAG_MASKED) ? a.n_eff[b * a.S + sc] : a.P;
+            if (n_eff < 0) n_eff = 0;
+            const int m = (a.flags & MUPS_FLAG_MASKED) ? min(n_eff + 1, a.P) : a.P;
+            const uint32_t bytes = (uint32_t)((12 * m + 15) & ~15);
+            const float* src = a.patches + (b * a.S + sc) * (int64_t)a.P * 3;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr32(bars + k)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr32(coords + (size_t)k * 3 * a.P)), "l"(src), "r"(bytes), "r"(smem_addr32(bars + k)) : "memory");
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < 2 && first + k < n_items; ++k) {
+        stats_separable_item<MODE, LOG_RES, 1, 1>(a, smem_raw, first + k, coords + (size_t)k * 3 * a.P, smem_addr32(bars + k));
+        __syncthreads();                           // the tables, the norms and s_fallback are reused by the next item
+    }
+}
+
 // =====================================================================================================
 // launchers
 // =====================================================================================================
@@ -857,7 +917,13 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         stats_separable_kernel<MODE, LOG, 1, STG><<<(unsigned)items, kSepThreads, smem, st>>>(a);                   \
     } while (0)
-        if (variant == 1) {                      // the round-1 kernel: packed products, sequential sums, shuffle staging
+        if (variant == 3 && log_res == 3 && patches != nullptr && a.g_sorted == nullptr && P % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(patches) & 15) == 0) {
+            // two items per CTA, patches by cp.async.bulk + mbarrier (benchmarking: profiles/README.md)
+            const size_t smem2 = smem + sizeof(float) * 3 * (size_t)a.P;
+            MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_pair_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            stats_separable_pair_kernel<1, 3><<<(unsigned)((items + 1) / 2), kSepThreads, smem2, st>>>(a, (int)items);
+        } else if (variant == 1) {                      // the round-1 kernel: packed products, sequential sums, shuffle staging
             if (log_res == 2) MUPS_LAUNCH_SEP(0, 2, 0);
             else if (log_res == 3) MUPS_LAUNCH_SEP(0, 3, 0);
             else if (log_res == 4) MUPS_LAUNCH_SEP(0, 4, 0);

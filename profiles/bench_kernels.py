@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import nesti_net_b200 as mb  # noqa: E402
 from nesti_net_b200 import _lib  # noqa: E402
-from oracle import mups_oracle as orc  # noqa: E402
+from nesti_net_b200 import synthetic as orc  # noqa: E402
 
 
 def timed(fn, iters=5, warm=2):
@@ -62,7 +62,8 @@ def main():
     reps = int(os.environ.get("REPS", 2))
     for rep in range(reps):
         for name, variant, fast in (("general", 0, False), ("sep_default_hybrid_pairsum_serialstage", 0, True),
-                                    ("sep_round1_packed_shufflestage", 1, True), ("sep_allscalar_pairsum_serialstage", 2, True)):
+                                    ("sep_round1_packed_shufflestage", 1, True), ("sep_allscalar_pairsum_serialstage", 2, True),
+                                    ("sep_two_items_per_cta_bulk_prefetch", 3, True)):
             if rep and name == "general":
                 continue
             if os.environ.get("ONLY") and str(variant) not in os.environ["ONLY"].split(","):

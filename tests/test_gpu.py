@@ -417,11 +417,12 @@ def test_half2_mups_layout_against_oracle(res, P, S, var, fastpath):
     assert np.array_equal(ch.transpose(0, 3, 1, 2).reshape(B, res, res, res, 20 * S), got.cpu().numpy())
 
 
-@pytest.mark.parametrize("variant,res,var", [(1, 8, 0.0156), (2, 8, 0.0156), (1, 4, 0.0625), (8, 16, 0.00390625),
+@pytest.mark.parametrize("variant,res,var", [(1, 8, 0.0156), (2, 8, 0.0156), (3, 8, 0.0156), (1, 4, 0.0625), (8, 16, 0.00390625),
                                              (1, 16, 0.00390625)])
 def test_half2_kernel_variants(variant, res, var):
     """The non-default statistics kernels kept for A/B measurements (mups_set_option "stats_variant": 1 = round-1
-    loop and staging, 2 = all-scalar loop, 8 = 16^3 without the cluster) compute the same features."""
+    loop and staging, 2 = all-scalar loop, 3 = two items per CTA with cp.async.bulk + mbarrier patch prefetch, 8 = 16^3
+    without the cluster) compute the same features."""
     w, mu, sg = grid_gmm(res, var)
     rng = np.random.RandomState(variant * 100 + res)
     P, S, B = 200, 2, 10
@@ -439,6 +440,12 @@ def test_half2_kernel_variants(variant, res, var):
     try:
         _lib.set_option("stats_variant", variant)
         got = mb.stats_3dmfv(pts, ne, gmm, S).cpu().numpy()
+        if variant == 3:        # same arithmetic, different staging of the patch: bit-identical, also for an odd item count
+            assert np.array_equal(got, base)
+            odd_pts, odd_ne = np.ascontiguousarray(pts[:3, :P]), np.ascontiguousarray(ne[:3, :1])      # 3 items: the last CTA has one
+            odd = mb.stats_3dmfv(odd_pts, odd_ne, gmm, 1).cpu().numpy()
+            _lib.set_option("stats_variant", 0)
+            assert np.array_equal(odd, mb.stats_3dmfv(odd_pts, odd_ne, gmm, 1).cpu().numpy())
     finally:
         _lib.set_option("stats_variant", 0)
     ref = c_oracle.mups(pts, ne, w, mu, sg, S)
