@@ -18,6 +18,8 @@
 //   bias + batch norm as scale / shift, ReLU, bf16 pack, 16-byte stores into a channel slice of the NDHWC output, so the
 //   inception module's concat costs nothing).
 // Every mbarrier wait is bounded: a barrier that never completes traps instead of hanging the GPU.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -37,6 +39,8 @@ struct ConvArgs {
     int kblocks;                     // ceil(Cin / 64)
     int n_tile;                      // output channels per CTA (multiple of 16, <= 256)
     int stages;
+    int m_sub;                       // 128-voxel tiles per CTA (2 when N <= 128: the weight tile is loaded once for both)
+    int m_tiles;                     // 128-voxel tiles of the whole batch
     int dz_box, b_box;               // z-slices / samples per 128-voxel tile
     int Cout;                        // output channels of this launch (rows of the weight tensor per tap)
     const float* scale;              // [Cout]
@@ -104,7 +108,8 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     // 1024-byte alignment of the stages (the swizzle pattern is a function of the shared-memory address bits)
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = a.n_tile * kTileK * 2;
-    const int stage_bytes = kABytes + b_bytes;
+    const int a_bytes = a.m_sub * kABytes;
+    const int stage_bytes = a_bytes + b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);      // full[stages], empty[stages], accumulator
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages), bar_acc = smem_u32(bars + 2 * kMaxStages);
@@ -128,44 +133,60 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    // this CTA's tile: 128 voxels x n_tile output channels
-    const int tile_m = blockIdx.x, n0 = blockIdx.y * a.n_tile;
+    // this CTA's tiles: m_sub x 128 voxels x n_tile output channels
+    const int n0 = blockIdx.y * a.n_tile;
     const int tiles_per_sample = (a.D * a.D * a.D + kTileM - 1) / kTileM;          // 4 for 8^3, else 1
-    const int b0 = tiles_per_sample > 1 ? tile_m / tiles_per_sample : tile_m * a.b_box;
-    const int z0 = tiles_per_sample > 1 ? (tile_m % tiles_per_sample) * a.dz_box : 0;
+    const int tile0 = blockIdx.x * a.m_sub;
+    int tb0[2], tz0[2];                          // first sample / first z-slice of each of this CTA's tiles (computed once: the
+    for (int u = 0; u < 2; ++u) {                // producer issues a load every ~100 ns and cannot afford divisions)
+        const int t = tile0 + u;
+        tb0[u] = tiles_per_sample > 1 ? t / tiles_per_sample : t * a.b_box;
+        tz0[u] = tiles_per_sample > 1 ? (t % tiles_per_sample) * a.dz_box : 0;
+    }
     const int taps = a.k * a.k * a.k;
     const int iters = taps * a.kblocks;
 
     if (warp == 0) {
         if (elect_one()) {
+            int s = 0, ph = 1, tap = 0, kb = 0, dz = 0, dy = 0, dx = 0;      // all counters advance incrementally
             for (int it = 0; it < iters; ++it) {
-                const int s = it % a.stages;
-                mbar_wait(bar_empty + 8 * s, ((it / a.stages) & 1) ^ 1);
-                const int tap = it / a.kblocks, kb = it - tap * a.kblocks;
-                const int dz = tap / (a.k * a.k), dy = (tap / a.k) % a.k, dx = tap % a.k;
+                mbar_wait(bar_empty + 8 * s, ph);
                 const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
                 mbar_expect_tx(bar_full + 8 * s, (uint32_t)stage_bytes);
-                tma_load_5d(dst, &map_x, bar_full + 8 * s, kb * kTileK, dx - a.pl, dy - a.pl, z0 + dz - a.pl, b0);
-                tma_load_3d(dst + kABytes, &map_w, bar_full + 8 * s, kb * kTileK, n0, tap);
+                tma_load_5d(dst, &map_x, bar_full + 8 * s, kb * kTileK, dx - a.pl, dy - a.pl, tz0[0] + dz - a.pl, tb0[0]);
+                if (a.m_sub == 2)                       // a tile past the end of the batch is all out of bounds: zero-filled
+                    tma_load_5d(dst + kABytes, &map_x, bar_full + 8 * s, kb * kTileK, dx - a.pl, dy - a.pl, tz0[1] + dz - a.pl, tb0[1]);
+                tma_load_3d(dst + a_bytes, &map_w, bar_full + 8 * s, kb * kTileK, n0, tap);
+                if (++s == a.stages) { s = 0; ph ^= 1; }
+                if (++kb == a.kblocks) {
+                    kb = 0; ++tap;
+                    if (++dx == a.k) { dx = 0; if (++dy == a.k) { dy = 0; ++dz; } }
+                }
             }
         }
     } else if (warp == 1) {
         // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        int s = 0, ph = 0;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % a.stages;
-            mbar_wait(bar_full + 8 * s, (it / a.stages) & 1);
+            mbar_wait(bar_full + 8 * s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t da = umma_desc(sa), db = umma_desc(sa + kABytes);
+                const uint64_t db = umma_desc(sa + a_bytes);
 #pragma unroll
-                for (int k = 0; k < kTileK / 16; ++k)       // UMMA_K = 16 bf16 = 32 bytes: +2 in the descriptor's 16-byte units
-                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                for (int u = 0; u < 2; ++u) {                // accumulator of tile u: TMEM columns [u n_tile, (u + 1) n_tile)
+                    if (u >= a.m_sub) break;
+                    const uint64_t da = umma_desc(sa + u * kABytes);
+#pragma unroll
+                    for (int k = 0; k < kTileK / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes: +2 in the descriptor's 16-byte units
+                        umma_bf16(tmem_base + (uint32_t)(u * a.n_tile), da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(bar_empty + 8 * s);              // frees the stage once these MMAs have read it
                 if (it == iters - 1) umma_commit(bar_acc);   // accumulator complete
             }
             __syncwarp();
+            if (++s == a.stages) { s = 0; ph ^= 1; }
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32 (w % 4), +32)
@@ -175,14 +196,17 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         const int m = quarter * 32 + lane;                 // row of the tile = voxel in box order (w fastest, then h, z, sample)
         const int W = a.D, HW = a.D * a.D;
         const int x = m % W, yy = (m / W) % a.D, zl = (m / HW) % a.dz_box, bl = m / (HW * a.dz_box);
-        const long long bsample = (long long)b0 + bl;
-        const bool live = bsample < a.B;
-        const long long voxel = ((bsample * a.D + (z0 + zl)) * a.D + yy) * a.D + x;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+        if (u >= a.m_sub) break;
+        const long long bsample = (long long)tb0[u] + bl;
+        const bool live = bsample < a.B && tile0 + u < a.m_tiles;
+        const long long voxel = ((bsample * a.D + (tz0[u] + zl)) * a.D + yy) * a.D + x;
         __nv_bfloat16* yrow = a.y ? a.y + voxel * a.y_stride + a.cout_off + n0 : nullptr;
         float* frow = a.y_f32 ? a.y_f32 + voxel * (long long)a.Cout + n0 : nullptr;
         for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
             uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(u * a.n_tile + c0), v);
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -213,6 +237,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                         if (n0 + c0 + j < a.Cout) frow[c0 + j] = f[j];
                 }
             }
+        }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -360,7 +385,14 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
     a.Cout = cout;
     a.scale = scale_dev; a.shift = shift_dev; a.relu = relu;
     a.y = static_cast<__nv_bfloat16*>(y_bf16_dev); a.y_stride = cout_total; a.cout_off = cout_off; a.y_f32 = y_f32_dev;
-    const int stage_bytes = kABytes + n_tile * kTileK * 2;
+    const long long m_tiles = vox >= kTileM ? (long long)B * (vox / kTileM) : (B + a.b_box - 1) / a.b_box;
+    MUPS_REQUIRE(m_tiles <= 0x7FFFFFFFll, "mups_conv3d_bn_relu: batch too large for one launch");
+    a.m_tiles = (int)m_tiles;
+    // two voxel tiles per CTA share one weight tile when both accumulators fit the 256 TMEM columns and the layer is deep
+    // enough for operand delivery to matter (g_conv_m_sub: benchmarking override)
+    a.m_sub = (n_tile <= 128 && m_tiles >= 2 * kNumSMs && k > 1) ? 2 : 1;
+    if (const char* e = getenv("MUPS_CONV_M_SUB")) a.m_sub = (atoi(e) == 2 && n_tile <= 128) ? 2 : 1;
+    const int stage_bytes = a.m_sub * kABytes + n_tile * kTileK * 2;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     a.stages = stages;
@@ -388,10 +420,9 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("mups_conv3d_bn_relu: weight tensor map rejected (CUresult %d)", (int)r); return MUPS_ERR_CUDA; }
     }
-    const long long m_tiles = vox >= kTileM ? (long long)B * (vox / kTileM) : (B + a.b_box - 1) / a.b_box;
-    MUPS_REQUIRE(m_tiles <= 0x7FFFFFFFll, "mups_conv3d_bn_relu: batch too large for one launch");
     MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3d_tcgen05_kernel<<<dim3((unsigned)m_tiles, (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
+    conv3d_tcgen05_kernel<<<dim3((unsigned)((m_tiles + a.m_sub - 1) / a.m_sub), (unsigned)(cout / n_tile)), kConvThreads, smem,
+                            static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;
 }
