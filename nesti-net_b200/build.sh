@@ -3,4 +3,4 @@
 set -e
 cd "$(dirname "$0")"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared "$@" \
-     -o libmups_b200.so csrc/mups_api.cu csrc/mups_index.cu csrc/mups_query.cu csrc/mups_stats.cu
+     -o libmups_b200.so csrc/*.cu

@@ -11,7 +11,13 @@ TF semantics reproduced: 'SAME' padding is asymmetric for even kernels (extra ce
 avg_pool3d 'SAME' divides by the number of valid cells, batch norm epsilon 1e-3 (evaluated with
 the moving statistics), the gate ends in ReLU -> softmax (:174-177), an expert sees the channel
 slice MuPS[..., 20*min(scales) : 20*min(scales) + 20*len(scales)] (:99-103) and its first inception
-module is round(128 / len(scales)) wide (:254).
+module is np.round(128 / divider) wide (:254) -- under the reference's Python 2.7 that `/` is an INTEGER division
+(42 for a three-scale expert, not 43).
+
+The architecture is pinned by the reference's own text: tests/golden/moe_tf_emulated.npz holds the outputs of
+get_model's network statements, scale_manager_net, conv_net_8g / _3g, normal_est_net and inception_module executed (with
+the tf_util layers) on a numpy emulation of the primitive TF ops; ``load_tf_variables`` restores the same variables by
+their TensorFlow names (tests/test_host.py::test_experts_net_against_reference_text_on_emulated_tf).
 """
 import numpy as np
 import torch
@@ -165,7 +171,7 @@ class ExpertsNormalEstimator(nn.Module):
         self.expert_fc = nn.ModuleList()
         for i in range(n_experts):
             scales = self.expert_dict[i]
-            conv = _ConvNet(20 * len(scales), res, int(np.round(128 / len(scales))), expert=True)
+            conv = _ConvNet(20 * len(scales), res, int(np.round(128 // len(scales))), expert=True)   # py2 `/` (:254)
             self.expert_conv.append(conv)
             self.expert_fc.append(nn.Sequential(FC(conv.out_features, 512), FC(512, 128), FC(128, 64),
                                                 FC(64, 3, bn=False, relu=False)))
@@ -180,12 +186,82 @@ class ExpertsNormalEstimator(nn.Module):
             normals.append(fc(conv(x[:, start:start + 20 * len(scales)])))
         return prob, torch.stack(normals)
 
+    def tf_variables(self):
+        """[(TensorFlow variable name, parameter / buffer, layout)] in the reference graph's naming
+        (tf_util.conv3d / fully_connected scopes under the `scope=` strings of models/experts_n_est.py:169-176,186-212,
+        254-285,296-307): '<scope>/weights', '/biases', '/bn/beta', '/bn/gamma', '/bn/moving_mean', '/bn/moving_variance'.
+        layout 'conv': TF [kd, kh, kw, Cin, Cout] -> torch [Cout, Cin, kd, kh, kw]; 'fc': TF [in, out] -> torch [out, in]."""
+        out = []
+
+        def bn(scope, m):
+            if m is not None:
+                out.extend([(scope + "/bn/beta", m.bias, None), (scope + "/bn/gamma", m.weight, None),
+                            (scope + "/bn/moving_mean", m.running_mean, None),
+                            (scope + "/bn/moving_variance", m.running_var, None)])
+
+        def convnet(net, scope_str):
+            it = iter(net.mods)
+            for layer, step in enumerate(net.plan, start=1):          # pools take a layer number too (:186-212)
+                if step is not None:
+                    continue
+                inc = next(it)
+                for suffix, c in (("_conv1", inc.one), ("_conv2", inc.a), ("_conv3", inc.b), ("_conv4", inc.pool)):
+                    scope = "inception%d%s%s" % (layer, scope_str, suffix)
+                    out.extend([(scope + "/weights", c.conv.weight, "conv"), (scope + "/biases", c.conv.bias, None)])
+                    bn(scope, c.bn)
+
+        def fcs(seq, scope_str):
+            for n, fc in enumerate(seq, start=1):
+                scope = "fc%d%s" % (n, scope_str)
+                out.extend([(scope + "/weights", fc.lin.weight, "fc"), (scope + "/biases", fc.lin.bias, None)])
+                bn(scope, fc.bn)
+
+        convnet(self.gate_conv, "gating_conv")
+        fcs(self.gate_fc, "noise")
+        res3 = any(step is not None and step[1] == 3 for step in self.gate_conv.plan)
+        for i, (conv, fc) in enumerate(zip(self.expert_conv, self.expert_fc)):
+            convnet(conv, "Expert_%d" % i + ("_expert_conv" if res3 else ""))     # :277
+            fcs(fc, "Expert_%d" % i)
+        return out
+
+    @torch.no_grad()
+    def load_tf_variables(self, get):
+        """Restore the network from the reference's variables: ``get(name)`` returns the array of TensorFlow variable
+        ``name`` (see ``tf_variables``; e.g. a dict exported from a checkpoint of train_n_est_w_experts.py, or
+        ``canonical_tf_names`` of one).  Raises KeyError / ValueError on a missing variable or a shape mismatch."""
+        for name, dst, layout in self.tf_variables():
+            a = torch.as_tensor(np.asarray(get(name)), dtype=dst.dtype)
+            if layout == "conv":
+                a = a.permute(4, 3, 0, 1, 2)
+            elif layout == "fc":
+                a = a.t()
+            if tuple(a.shape) != tuple(dst.shape):
+                raise ValueError("variable %s has shape %s, the network expects %s" % (name, tuple(a.shape), tuple(dst.shape)))
+            dst.copy_(a)
+        return self
+
     @torch.no_grad()
     def predict(self, mups):
         """What test_n_est_w_experts.py:148-152 keeps: the normal of the most probable expert."""
         prob, n_est = self.forward(mups)
         expert = prob.argmax(dim=0)
         return n_est[expert, torch.arange(n_est.shape[1], device=n_est.device)], expert, prob.transpose(0, 1)
+
+
+def canonical_tf_names(variables):
+    """{checkpoint name: array} -> the same arrays under the names ``tf_variables`` uses.  TensorFlow 1.x stores the shadow
+    variables of tf.train.ExponentialMovingAverage (tf_util.py:474-490) as
+    '<scope>/bn/<scope>/bn/moments/Squeeze/ExponentialMovingAverage' (mean) and '.../Squeeze_1/ExponentialMovingAverage'
+    (variance); everything else keeps its name."""
+    out = {}
+    for name, a in variables.items():
+        name = name[:-2] if name.endswith(":0") else name
+        if name.endswith("/ExponentialMovingAverage"):
+            head = name.split("/bn/")[0]
+            leaf = "moving_variance" if "Squeeze_1" in name else "moving_mean"
+            name = head + "/bn/" + leaf
+        out[name] = a
+    return out
 
 
 def angular_rms_deg(n_a, n_b):

@@ -29,6 +29,11 @@ half2_tf_emulated.npz -- outputs of the reference's own TensorFlow source text
     `tf` bound to tests/golden/tf1_emulation.py (numpy emulation of the
     primitive TF ops): the mask stage and the anisotropic prefactor run as the
     reference wrote them.
+moe_tf_emulated.npz -- outputs of the reference's own NETWORK text (get_model's
+    statements after the MuPS loop, scale_manager_net, conv_net_8g / _3g,
+    normal_est_net, inception_module and the tf_util layers) run on
+    tests/golden/tf1_emulation_nn.py with variables from tests/golden/moe_weights.py:
+    pins the architecture of the consumer (experts_net.py, moe_engine.py).
 half2_oracle.npz -- inputs/outputs of the recorded fp32 transliteration of
     utils/tf_util.py:655-753 / :578-652 (TensorFlow 1.12 is not installable:
     PARITY UNPINNED), written only after the independent float64 restatement
@@ -469,6 +474,90 @@ def make_half2_tf_emulated():
     print("tf-emulated MuPS %s" % (mups.shape,))
 
 
+def _reference_function_text(path, name):
+    """Source text of top-level function `name`, cut out TEXTUALLY (from its `def` line to the next top-level statement):
+    models/experts_n_est.py as shipped does not parse (unbalanced parenthesis at :103), so `ast` cannot be used on it."""
+    lines = open(path).read().split("\n")
+    first = next(i for i, ln in enumerate(lines) if ln.startswith("def %s(" % name))
+    last = next((i for i, ln in enumerate(lines) if i > first and ln[:1] not in ("", " ", "\t", "#", "\r")), len(lines))
+    return "\n".join(ln.rstrip("\r") for ln in lines[first:last])
+
+
+def _reference_network_statements(path):
+    """The network statements of models/experts_n_est.py::get_model (:78-106): from `experts_prob = scale_manager_net(`
+    to `n_est = tf.stack(experts)`, as written in the reference -- except that ONE closing parenthesis is removed from the
+    `experts.append(normal_est_net(...` statement (:102-103), which has one too many as shipped (a syntax error)."""
+    lines = open(path).read().split("\n")
+    top = next(i for i, ln in enumerate(lines) if ln.startswith("def get_model("))
+    first = next(i for i, ln in enumerate(lines) if i > top and ln.strip().startswith("experts_prob = scale_manager_net("))
+    last = next(i for i, ln in enumerate(lines) if i > first and ln.strip().startswith("n_est = tf.stack(experts)"))
+    pad = len(lines[first]) - len(lines[first].lstrip())
+    body = [ln.rstrip("\r")[pad:] if ln.strip() else "" for ln in lines[first:last + 1]]
+    bad = [i for i, ln in enumerate(body) if ln.rstrip().endswith("divider=len(expert_dict[i]))))")]
+    assert len(bad) == 1, "the reference's syntax error is expected exactly once"
+    body[bad[0]] = body[bad[0]].rstrip()[:-1]
+    return "\n".join(body)
+
+
+def make_moe_tf_emulated():
+    """moe_tf_emulated.npz: the REFERENCE'S OWN network code -- the statements of get_model after the MuPS loop
+    (models/experts_n_est.py:78-106: gate, default expert assignment, channel slices, experts), scale_manager_net,
+    conv_net_8g, conv_net_3g, normal_est_net, inception_module (:155-310) and the layers they call in utils/tf_util.py
+    (conv3d, fully_connected, max_pool3d, avg_pool3d, batch_norm_template, batch_norm_for_conv3d / _fc and the variable
+    helpers) -- executed statement for statement with `tf` bound to tests/golden/tf1_emulation_nn.py, is_training = False,
+    variables restored by name from tests/golden/moe_weights.py.  Python-2 semantics are kept where the text relies on them
+    (`128 / divider` is an integer division).  Pins the architecture of nesti-net_b200/experts_net.py (and through it the
+    tensor-core engine) against the reference's text instead of a reading of it."""
+    import types
+    sys.path.insert(0, HERE)
+    import tf1_emulation_nn as tf
+    import moe_weights  # noqa: F401
+    util_ns = {"tf": tf, "np": np}
+    for fn in ("_variable_on_cpu", "_variable_with_weight_decay", "conv3d", "fully_connected", "max_pool3d", "avg_pool3d",
+               "batch_norm_template", "batch_norm_for_fc", "batch_norm_for_conv3d"):
+        exec(compile(_reference_function_source("/root/reference/utils/tf_util.py", fn), "tf_util.py::" + fn, "exec"), util_ns)
+    tf_util = types.SimpleNamespace(**{k: v for k, v in util_ns.items() if callable(v) and k not in ("tf", "np")})
+    model = "/root/reference/models/experts_n_est.py"
+    py2_len = lambda x: tf.Py2Int(len(x))                       # noqa: E731  (so that `128 / divider` floors, as under 2.7)
+    net_ns = {"tf": tf, "np": np, "tf_util": tf_util, "len": py2_len}
+    for fn in ("scale_manager_net", "conv_net_8g", "conv_net_3g", "normal_est_net", "inception_module"):
+        exec(compile(_reference_function_text(model, fn), "experts_n_est.py::" + fn, "exec"), net_ns)
+    statements = compile(_reference_network_statements(model), "experts_n_est.py::get_model[network]", "exec")
+
+    rng = np.random.RandomState(2018)
+    out = {}
+    cases = {"g3": dict(res=3, var=0.11, n_rads=2, n_experts=3, B=4),
+             "g3s3": dict(res=3, var=0.11, n_rads=3, n_experts=4, B=3),      # a three-scale expert: 128 / 3 under Python 2
+             "g8": dict(res=8, var=0.0156, n_rads=4, n_experts=7, B=2)}     # the Nesti-Net default
+    for name, c in cases.items():
+        w, mu, sg = orc.gmm_feed(*orc.get_3d_grid_gmm([c["res"]] * 3, c["var"]))
+        P, B, S = 48, c["B"], c["n_rads"]
+        pts = np.zeros((B, S * P, 3), np.float32)
+        ne = rng.randint(P // 3, P + 1, size=(B, S)).astype(np.int32)
+        for b in range(B):
+            for s_ in range(S):
+                x = rng.normal(size=(ne[b, s_], 3)) * rng.uniform(0.2, 0.6)
+                x /= np.maximum(1.0, np.linalg.norm(x, axis=1, keepdims=True))
+                pts[b, s_ * P:s_ * P + ne[b, s_]] = x
+        mups = orc.mups_assemble(pts, w, mu, sg, ne, S).astype(np.float32)
+        tf.reset_graph()
+        env = dict(net_ns)
+        env.update({"MuPS": tf.Tensor(mups), "bn_decay": None, "is_training": tf.Tensor(np.bool_(False)),
+                    "weight_decay": 0.005, "n_experts": c["n_experts"], "n_gaussians": tf.Py2Int(len(w)),
+                    "n_rads": tf.Py2Int(S), "expert_dict": None})
+        exec(statements, env)
+        prob, n_est = env["experts_prob"].a, env["n_est"].a
+        assert prob.shape == (c["n_experts"], B) and n_est.shape == (c["n_experts"], B, 3)
+        assert np.allclose(prob.sum(axis=0), 1.0, atol=1e-6) and np.all(np.isfinite(n_est))
+        names = sorted(tf.created_variables)
+        out.update({name + "_mups": mups, name + "_experts_prob": prob, name + "_n_est": n_est,
+                    name + "_n_rads": np.int32(S), name + "_n_experts": np.int32(c["n_experts"]),
+                    name + "_variables": np.array(["%s %s" % (n, "x".join(map(str, tf.created_variables[n]))) for n in names])})
+        print("tf-emulated MoE %s: %d variables, %.1f M parameters, prob %s, n_est %s"
+              % (name, len(names), sum(int(np.prod(tf.created_variables[n])) for n in names) / 1e6, prob.shape, n_est.shape))
+    np.savez_compressed(os.path.join(HERE, "moe_tf_emulated.npz"), **out)
+
+
 def make_rotation_reference():
     """utils/eulerangles.py::euler2mat and the augmentation of train_n_est_w_experts.py:262-272 run on the
     unmodified reference module (a py2 builtin, ``reduce``, is supplied from functools)."""
@@ -504,3 +593,4 @@ if __name__ == "__main__":
     make_rotation_reference()
     make_half2()
     make_half2_tf_emulated()
+    make_moe_tf_emulated()

@@ -1014,6 +1014,48 @@ def test_tensor_core_consumer_against_fp32_network():
     assert tuple(sel.shape) == (len(q), 3) and tuple(probs.shape) == (len(q), 7) and torch.equal(expert, prob.argmax(0))
 
 
+def test_tensor_core_consumer_against_reference_text(golden_dir):
+    """The tcgen05 engine against the outputs of the REFERENCE'S OWN network text run on the emulated TF ops
+    (tests/golden/moe_tf_emulated.npz, case g8: 4 scales, 7 experts, 8^3; variables restored by their TensorFlow names
+    with ExpertsNormalEstimator.load_tf_variables): every expert's normal within 1 degree, gate probabilities within 0.02,
+    the same expert chosen -- and the fp32 network on the GPU within 1e-3 degrees of the same fixture."""
+    import sys
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg
+    from nesti_net_b200.moe_engine import TensorCoreExperts
+    if golden_dir not in sys.path:
+        sys.path.insert(0, golden_dir)
+    import moe_weights
+    g = np.load(os.path.join(golden_dir, "moe_tf_emulated.npz"))
+    mups = torch.from_numpy(g["g8_mups"]).cuda()
+    net = ExpertsNormalEstimator(4, 512, 7).eval()
+    table = {n: (d, l) for n, d, l in net.tf_variables()}
+
+    def get(name):
+        d, layout = table[name]
+        shp = tuple(d.shape)
+        shp = shp[2:] + (shp[1], shp[0]) if layout == "conv" else shp[::-1] if layout == "fc" else shp
+        return moe_weights.variable_value(name, shp)
+    net.load_tf_variables(get)
+    net = net.cuda()
+    ref_prob, ref_n = torch.from_numpy(g["g8_experts_prob"]).cuda(), torch.from_numpy(g["g8_n_est"]).cuda()
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            prob32, n32 = net(mups)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    rms32 = angular_rms_deg(n32.reshape(-1, 3), ref_n.reshape(-1, 3))
+    prob, n_est = TensorCoreExperts(net).forward(mups)
+    torch.cuda.synchronize()
+    rms = angular_rms_deg(n_est.reshape(-1, 3), ref_n.reshape(-1, 3))
+    dprob = float((prob - ref_prob).abs().max())
+    print("vs the reference's network text: fp32 network %.3g deg, tensor-core engine %.3g deg, max |dprob| %.3g"
+          % (rms32, rms, dprob))
+    assert rms32 < 1e-3 and float((prob32 - ref_prob).abs().max()) < 1e-4
+    assert rms < 1.0 and dprob < 0.02 and torch.equal(prob.argmax(0), ref_prob.argmax(0))
+
+
 def test_downstream_moe_normals():
     """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
     models/experts_n_est.py, fp32) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4 angular

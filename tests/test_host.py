@@ -308,3 +308,52 @@ def test_experts_net_tf_semantics_cpu():
     assert angular_rms_deg(normal, -normal) < 1e-9 and abs(angular_rms_deg(torch.tensor([[1., 0, 0]]), torch.tensor([[0., 1, 0]])) - 90) < 1e-9
     with pytest.raises(ValueError):
         ExpertsNormalEstimator(n_rads=2, n_gaussians=125)
+
+
+def _restore_reference_variables(net, golden_dir):
+    import sys
+    if golden_dir not in sys.path:
+        sys.path.insert(0, golden_dir)
+    import moe_weights
+    shapes = {}
+
+    def get(name):
+        dst = next(d for n, d, _ in net.tf_variables() if n == name)
+        layout = next(l for n, _, l in net.tf_variables() if n == name)
+        shp = tuple(dst.shape)
+        if layout == "conv":
+            shp = shp[2:] + (shp[1], shp[0])
+        elif layout == "fc":
+            shp = shp[::-1]
+        shapes[name] = shp
+        return moe_weights.variable_value(name, shp)
+    net.load_tf_variables(get)
+    return shapes
+
+
+@pytest.mark.parametrize("case", ["g3", "g3s3", "g8"])
+def test_experts_net_against_reference_text_on_emulated_tf(golden_dir, case):
+    """experts_net.ExpertsNormalEstimator against the REFERENCE'S OWN network text (models/experts_n_est.py:78-106,155-310
+    with the layers of utils/tf_util.py:254-351,406-495) executed on the numpy emulation of the primitive TF ops
+    (tests/golden/moe_tf_emulated.npz, make_golden.py::make_moe_tf_emulated): the variables the reference's graph creates
+    (names and shapes), the gate probabilities and every expert's normal.  g3s3 has a three-scale expert, whose width is
+    128 / 3 = 42 under the reference's Python 2; g8 is the Nesti-Net default (4 scales, 7 experts, 8^3)."""
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg, canonical_tf_names
+    g = np.load(os.path.join(golden_dir, "moe_tf_emulated.npz"))
+    mups = torch.from_numpy(g[case + "_mups"])
+    net = ExpertsNormalEstimator(int(g[case + "_n_rads"]), int(np.prod(mups.shape[1:4])), int(g[case + "_n_experts"])).eval()
+    shapes = _restore_reference_variables(net, golden_dir)
+    ours = sorted("%s %s" % (n, "x".join(map(str, s))) for n, s in shapes.items())
+    assert ours == sorted(g[case + "_variables"].tolist()), "variable names / shapes differ from the reference graph's"
+    with torch.no_grad():
+        prob, n_est = net(mups)
+    ref_prob, ref_n = g[case + "_experts_prob"], g[case + "_n_est"]
+    assert np.allclose(prob.numpy(), ref_prob, rtol=1e-4, atol=1e-6), float(np.abs(prob.numpy() - ref_prob).max())
+    scale = float(np.abs(ref_n).max())
+    assert np.allclose(n_est.numpy(), ref_n, rtol=1e-4, atol=1e-4 * scale), float(np.abs(n_est.numpy() - ref_n).max())
+    assert angular_rms_deg(n_est.reshape(-1, 3), torch.from_numpy(ref_n).reshape(-1, 3)) < 1e-2
+    assert np.array_equal(prob.numpy().argmax(0), ref_prob.argmax(0))
+    # a real TF 1.x checkpoint names the moving statistics after the ExponentialMovingAverage shadow variables
+    ck = {"fc1noise/bn/fc1noise/bn/moments/Squeeze/ExponentialMovingAverage:0": 1,
+          "fc1noise/bn/fc1noise/bn/moments/Squeeze_1/ExponentialMovingAverage": 2, "fc1noise/weights": 3}
+    assert canonical_tf_names(ck) == {"fc1noise/bn/moving_mean": 1, "fc1noise/bn/moving_variance": 2, "fc1noise/weights": 3}
