@@ -81,7 +81,10 @@ int64_t mups_launch_count(void);
  * "query_kernel" (0 = automatic: hierarchical for indices with >= 6 Morton bits per axis, i.e. fine grids; 1 = flat
  * cell scan; 2 = hierarchical), "query_order" (0 = automatic; 1 = CTAs in caller order; 2 = CTAs in Morton order of the
  * centres) and "hier_margin" (-1 = automatic; extra expected candidates above P kept by the hierarchical kernel's key
- * threshold; tests set 0 to exercise the hand-over to the flat kernel): results never depend on any of them. */
+ * threshold; tests set 0 to exercise the hand-over to the flat kernel): results never depend on any of them.
+ * "pool_variant" (0 = automatic: shared-memory tile + separable box sum for the 8^3 average pools; 1 = the per-voxel
+ * kernel everywhere) and "conv_variant" (0 = automatic: two CTAs per SM for the short-K 1^3 layers; 1 = always one CTA per
+ * SM with the deepest pipeline): benchmarking only. */
 int mups_set_option(const char* name, int64_t value);
 
 /* ---- spatial index (K1 bbox + K2 grid build) --------------------------------------------- */

@@ -102,6 +102,64 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+
+// Epilogue of both convolution kernels: the four epilogue warps read their 32 TMEM lanes x 16 columns at a time, apply
+// scale / shift (+ ReLU), pack to bf16 and store into the channel slice of the NDHWC output (and / or the fp32 output).
+__device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_acc, uint32_t tmem_base, int warp, int lane, int n0, int tile0,
+                                              const int (&tb0)[2], const int (&tz0)[2]) {
+    // warp w may touch TMEM lanes [32 (w % 4), +32)
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;                 // row of the tile = voxel in box order (w fastest, then h, z, sample)
+    const int W = a.D, HW = a.D * a.D;
+    const int x = m % W, yy = (m / W) % a.D, zl = (m / HW) % a.dz_box, bl = m / (HW * a.dz_box);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+    if (u >= a.m_sub) break;
+    const long long bsample = (long long)tb0[u] + bl;
+    const bool live = bsample < a.B && tile0 + u < a.m_tiles;
+    const long long voxel = ((bsample * a.D + (tz0[u] + zl)) * a.D + yy) * a.D + x;
+    __nv_bfloat16* yrow = a.y ? a.y + voxel * a.y_stride + a.cout_off + n0 : nullptr;
+    float* frow = a.y_f32 ? a.y_f32 + voxel * (long long)a.Cout + n0 : nullptr;
+    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(u * a.n_tile + c0), v);
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int co = n0 + c0 + j;
+            const float sc = co < a.Cout ? __ldg(a.scale + co) : 0.f, sh = co < a.Cout ? __ldg(a.shift + co) : 0.f;
+            float t = fmaf(__uint_as_float(v[j]), sc, sh);
+            f[j] = a.relu ? fmaxf(t, 0.f) : t;
+        }
+        if (live) {
+            if (yrow) {
+                uint4 lo, hi;
+                __nv_bfloat162 p;
+                p = __floats2bfloat162_rn(f[0], f[1]);   lo.x = *reinterpret_cast<uint32_t*>(&p);
+                p = __floats2bfloat162_rn(f[2], f[3]);   lo.y = *reinterpret_cast<uint32_t*>(&p);
+                p = __floats2bfloat162_rn(f[4], f[5]);   lo.z = *reinterpret_cast<uint32_t*>(&p);
+                p = __floats2bfloat162_rn(f[6], f[7]);   lo.w = *reinterpret_cast<uint32_t*>(&p);
+                p = __floats2bfloat162_rn(f[8], f[9]);   hi.x = *reinterpret_cast<uint32_t*>(&p);
+                p = __floats2bfloat162_rn(f[10], f[11]); hi.y = *reinterpret_cast<uint32_t*>(&p);
+                p = __floats2bfloat162_rn(f[12], f[13]); hi.z = *reinterpret_cast<uint32_t*>(&p);
+                p = __floats2bfloat162_rn(f[14], f[15]); hi.w = *reinterpret_cast<uint32_t*>(&p);
+                uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+                dst[0] = lo;
+                dst[1] = hi;
+            }
+            if (frow) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + c0 + j < a.Cout) frow[c0 + j] = f[j];
+            }
+        }
+    }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -189,57 +247,149 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             if (++s == a.stages) { s = 0; ph ^= 1; }
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes [32 (w % 4), +32)
-        mbar_wait(bar_acc, 0);
+        conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
+    }
+    __syncthreads();
+    if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quarter = warp & 3;
-        const int m = quarter * 32 + lane;                 // row of the tile = voxel in box order (w fastest, then h, z, sample)
-        const int W = a.D, HW = a.D * a.D;
-        const int x = m % W, yy = (m / W) % a.D, zl = (m / HW) % a.dz_box, bl = m / (HW * a.dz_box);
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- z-halo variant for the 8^3 volumes (the layers that carry 85 % of the network's arithmetic) -----------------------------
+// The kernel above re-reads the activation tile from L2 once per tap and sits at the L2 -> SM throughput cap.  A shift of
+// the window by one z-slice is a shift by 64 rows = 8 swizzle atoms of the K-major shared-memory tile, i.e. a LEGAL operand
+// start address.  So for every (dy, dx, 64-channel block) this kernel loads ONE box of 4 + k - 1 z-slices (the CTA's four
+// slices = two 128-voxel tiles, plus the halo; out-of-volume slices / rows / columns zero-filled by the TMA unit) and issues
+// the MMAs of all k dz-taps of both tiles from it, the descriptor start advanced by (2 u + dz) * 8 KB.  Activation traffic per
+// tap falls from 32 KB to (4 + k - 1) * 8 / k KB (12.8 KB at k = 5); the weights stream through their own ring.
+struct HaloArgs { int na, nb, a_box_bytes, swap; };   // A stages, B stages, bytes of one activation box, operand roles swapped
+
+// Epilogue of the z-halo kernel with SWAPPED operand roles (accumulator = [128 output channels (TMEM lanes)] x [256 voxels
+// (columns)]): a thread owns one output channel, a warp's store covers 32 consecutive channels of one voxel (64 bytes).
+__device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_t bar_acc, uint32_t tmem_base, int warp, int lane, int n0,
+                                                      long long voxel0) {
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3;
+    const int co = n0 + quarter * 32 + lane;
+    const bool real = co < a.Cout;
+    const float sc = real ? __ldg(a.scale + co) : 0.f, sh = real ? __ldg(a.shift + co) : 0.f;
+    __nv_bfloat16* ycol = a.y ? a.y + voxel0 * a.y_stride + a.cout_off + co : nullptr;
+    float* fcol = a.y_f32 ? a.y_f32 + voxel0 * (long long)a.Cout + co : nullptr;
+    for (int j0 = 0; j0 < 256; j0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)j0, v);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-        if (u >= a.m_sub) break;
-        const long long bsample = (long long)tb0[u] + bl;
-        const bool live = bsample < a.B && tile0 + u < a.m_tiles;
-        const long long voxel = ((bsample * a.D + (tz0[u] + zl)) * a.D + yy) * a.D + x;
-        __nv_bfloat16* yrow = a.y ? a.y + voxel * a.y_stride + a.cout_off + n0 : nullptr;
-        float* frow = a.y_f32 ? a.y_f32 + voxel * (long long)a.Cout + n0 : nullptr;
-        for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(u * a.n_tile + c0), v);
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int co = n0 + c0 + j;
-                const float sc = co < a.Cout ? __ldg(a.scale + co) : 0.f, sh = co < a.Cout ? __ldg(a.shift + co) : 0.f;
-                float t = fmaf(__uint_as_float(v[j]), sc, sh);
-                f[j] = a.relu ? fmaxf(t, 0.f) : t;
-            }
-            if (live) {
-                if (yrow) {
-                    uint4 lo, hi;
-                    __nv_bfloat162 p;
-                    p = __floats2bfloat162_rn(f[0], f[1]);   lo.x = *reinterpret_cast<uint32_t*>(&p);
-                    p = __floats2bfloat162_rn(f[2], f[3]);   lo.y = *reinterpret_cast<uint32_t*>(&p);
-                    p = __floats2bfloat162_rn(f[4], f[5]);   lo.z = *reinterpret_cast<uint32_t*>(&p);
-                    p = __floats2bfloat162_rn(f[6], f[7]);   lo.w = *reinterpret_cast<uint32_t*>(&p);
-                    p = __floats2bfloat162_rn(f[8], f[9]);   hi.x = *reinterpret_cast<uint32_t*>(&p);
-                    p = __floats2bfloat162_rn(f[10], f[11]); hi.y = *reinterpret_cast<uint32_t*>(&p);
-                    p = __floats2bfloat162_rn(f[12], f[13]); hi.z = *reinterpret_cast<uint32_t*>(&p);
-                    p = __floats2bfloat162_rn(f[14], f[15]); hi.w = *reinterpret_cast<uint32_t*>(&p);
-                    uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-                    dst[0] = lo;
-                    dst[1] = hi;
+        for (int j = 0; j < 16; ++j) {
+            float t = fmaf(__uint_as_float(v[j]), sc, sh);
+            t = a.relu ? fmaxf(t, 0.f) : t;
+            if (ycol) ycol[(long long)(j0 + j) * a.y_stride] = __float2bfloat16_rn(t);
+            if (fcol && real) fcol[(long long)(j0 + j) * a.Cout] = t;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvArgs a, const HaloArgs h) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.n_tile * kTileK * 2;
+    unsigned char* smem_b = smem + (size_t)h.na * h.a_box_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)h.nb * b_bytes);   // a_full[2], a_empty[2], b_full[8], b_empty[8], accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kMaxStages + 1);
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 2), bar_bfull = smem_u32(bars + 4),
+                   bar_bempty = smem_u32(bars + 4 + kMaxStages), bar_acc = smem_u32(bars + 4 + 2 * kMaxStages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this CTA: sample blockIdx.x / 2, z-slices [4 (blockIdx.x & 1), +4) = tiles 2 blockIdx.x, 2 blockIdx.x + 1; n_tile channels at n0
+    const int n0 = blockIdx.y * a.n_tile;
+    const int tile0 = blockIdx.x * 2;
+    const int tb0[2] = {(int)(blockIdx.x >> 1), (int)(blockIdx.x >> 1)};
+    const int tz0[2] = {(int)(blockIdx.x & 1) * 4, (int)(blockIdx.x & 1) * 4 + 2};
+    const int steps = a.kblocks * a.k * a.k;            // (64-channel block, dy, dx)
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int sa = 0, pa = 1, sb = 0, pb = 1, kb = 0, dy = 0, dx = 0;
+            for (int st = 0; st < steps; ++st) {
+                mbar_wait(bar_aempty + 8 * sa, pa);
+                mbar_expect_tx(bar_afull + 8 * sa, (uint32_t)h.a_box_bytes);
+                tma_load_5d(smem_u32(smem + (size_t)sa * h.a_box_bytes), &map_x, bar_afull + 8 * sa, kb * kTileK, dx - a.pl, dy - a.pl,
+                            tz0[0] - a.pl, tb0[0]);
+                if (++sa == h.na) { sa = 0; pa ^= 1; }
+                for (int dz = 0; dz < a.k; ++dz) {
+                    mbar_wait(bar_bempty + 8 * sb, pb);
+                    mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_bytes);
+                    tma_load_3d(smem_u32(smem_b + (size_t)sb * b_bytes), &map_w, bar_bfull + 8 * sb, kb * kTileK, n0, (dz * a.k + dy) * a.k + dx);
+                    if (++sb == h.nb) { sb = 0; pb ^= 1; }
                 }
-                if (frow) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (n0 + c0 + j < a.Cout) frow[c0 + j] = f[j];
-                }
+                if (++dx == a.k) { dx = 0; if (++dy == a.k) { dy = 0; ++kb; } }
             }
         }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        const uint32_t idesc_swapped = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int sa = 0, pa = 0, sb = 0, pb = 0;
+        for (int st = 0; st < steps; ++st) {
+            mbar_wait(bar_afull + 8 * sa, pa);
+            const uint32_t abase = smem_u32(smem + (size_t)sa * h.a_box_bytes);
+            for (int dz = 0; dz < a.k; ++dz) {
+                mbar_wait(bar_bfull + 8 * sb, pb);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t db = umma_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
+                    if (h.swap) {
+                        // D^T[128 channels x 256 voxels] += W[128 x 64] * X[256 x 64]^T: ONE N = 256 MMA per K step covers both
+                        // voxel tiles (box slices dz .. dz + 3 are 256 contiguous rows): 12 KB of operand reads per 128
+                        // tensor cycles instead of 16 KB for two N = 128 MMAs
+                        const uint64_t dxv = umma_desc(abase + (uint32_t)dz * 8192u);
+#pragma unroll
+                        for (int k = 0; k < kTileK / 16; ++k)
+                            umma_bf16(tmem_base, db + 2 * k, dxv + 2 * k, idesc_swapped, (st > 0 || dz > 0 || k > 0) ? 1u : 0u);
+                    } else
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {            // tile u = slices 2u, 2u + 1 of the CTA; tap dz reads box slices 2u + dz, +1
+                        const uint64_t da = umma_desc(abase + (uint32_t)(2 * u + dz) * 8192u);
+#pragma unroll
+                        for (int k = 0; k < kTileK / 16; ++k)
+                            umma_bf16(tmem_base + (uint32_t)(u * a.n_tile), da + 2 * k, db + 2 * k, idesc, (st > 0 || dz > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(bar_bempty + 8 * sb);
+                    if (dz == a.k - 1) {
+                        umma_commit(bar_aempty + 8 * sa);    // the box is free once the MMAs of its last tap have read it
+                        if (st == steps - 1) umma_commit(bar_acc);
+                    }
+                }
+                __syncwarp();
+                if (++sb == h.nb) { sb = 0; pb ^= 1; }
+            }
+            if (++sa == h.na) { sa = 0; pa ^= 1; }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else if (h.swap) {
+        conv_epilogue_swapped(a, bar_acc, tmem_base, warp, lane, n0, (long long)tb0[0] * 512 + tz0[0] * 64);
+    } else {
+        conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
     }
     __syncthreads();
     if (warp == 2) {
@@ -309,6 +459,82 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const __nv_bfloat16* __rest
     }
 }
 
+// The same average pool for the 8^3 volumes of the reference's networks (the 27-tap version above re-reads every input
+// voxel 27 times through L2: 20 % of the whole forward pass).  One CTA = one sample x 32 channels: the 512 x 32 tile is staged
+// once in shared memory as fp32 (64 KB) and the box sum is done SEPARABLY in place -- three passes of 64 lines of 8 voxels,
+// one warp per line, lane = channel (bank-conflict free) -- then scaled by 1 / (valid cells) = 1 / (cx cy cz) and stored.
+// HBM traffic: every input and output byte once.
+template <int K>
+__global__ void __launch_bounds__(256) avgpool8_tile_kernel(const __nv_bfloat16* __restrict__ x, int ct, int c_off, int c,
+                                                            __nv_bfloat16* __restrict__ y) {
+    extern __shared__ __align__(16) float tile[];                  // [512 voxels][32 channels]
+    constexpr int D = 8, PL = (K - 1) / 2;
+    const int chunks = c >> 5;
+    const long long b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x % chunks;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __nv_bfloat16* src = x + b * 512 * (long long)ct + c_off + chunk * 32;
+    for (int i = tid; i < 512 * 4; i += 256) {                     // 16-byte loads: 4 per voxel
+        const int v = i >> 2, part = i & 3;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + v * (long long)ct) + part);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+        float4* dst = reinterpret_cast<float4*>(tile + v * 32 + part * 8);
+        dst[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+        dst[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        // line l of pass 0 (along x): voxels (l * 8 + i); pass 1 (along y): z = l / 8, x = l % 8; pass 2 (along z): y = l / 8, x = l % 8
+        const int step = pass == 0 ? 1 : pass == 1 ? 8 : 64;
+        for (int l = warp; l < 64; l += 8) {
+            const int base = pass == 0 ? l * 8 : pass == 1 ? (l >> 3) * 64 + (l & 7) : l;
+            float r[D], o[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) r[i] = tile[(base + i * step) * 32 + lane];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    const int j = i + d - PL;
+                    if (j >= 0 && j < D) acc += r[j];
+                }
+                o[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) tile[(base + i * step) * 32 + lane] = o[i];
+        }
+        __syncthreads();
+    }
+    __nv_bfloat16* dst = y + b * 512 * (long long)c + chunk * 32;
+    for (int i = tid; i < 512 * 4; i += 256) {
+        const int v = i >> 2, part = i & 3;
+        const int vx = v & 7, vy = (v >> 3) & 7, vz = v >> 6;
+        auto valid = [](int q) { return min(q - PL + K - 1, D - 1) - max(q - PL, 0) + 1; };
+        const float inv = 1.f / (float)(valid(vx) * valid(vy) * valid(vz));
+        const float4* sp = reinterpret_cast<const float4*>(tile + v * 32 + part * 8);
+        const float4 a0 = sp[0], a1 = sp[1];
+        uint4 out;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
+        o2[0] = __floats2bfloat162_rn(a0.x * inv, a0.y * inv);
+        o2[1] = __floats2bfloat162_rn(a0.z * inv, a0.w * inv);
+        o2[2] = __floats2bfloat162_rn(a1.x * inv, a1.y * inv);
+        o2[3] = __floats2bfloat162_rn(a1.z * inv, a1.w * inv);
+        reinterpret_cast<uint4*>(dst + v * (long long)c)[part] = out;
+    }
+}
+
+template <int K>
+static cudaError_t launch_avgpool8(const __nv_bfloat16* x, long long B, int ct, int c_off, int c, __nv_bfloat16* y, cudaStream_t st) {
+    constexpr int smem = 512 * 32 * 4;
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(avgpool8_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    avgpool8_tile_kernel<K><<<(unsigned)(B * (c >> 5)), 256, smem, st>>>(x, ct, c_off, c, y);
+    return cudaGetLastError();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -348,6 +574,17 @@ int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off
     MUPS_REQUIRE(B >= 1 && (D == 2 || D == 4 || D == 8), "mups_pool3d: B=%lld, volume edge %d", (long long)B, D);
     MUPS_REQUIRE(c >= 8 && c % 8 == 0 && c_total % 8 == 0 && c_off % 8 == 0 && c_off + c <= c_total, "mups_pool3d: channels (%d of %d at %d) must be multiples of 8", c, c_total, c_off);
     MUPS_REQUIRE(is_max ? k == 2 : (k >= 1 && k <= 5), "mups_pool3d: window %d", k);
+    if (!is_max && D == 8 && k >= 2 && c % 32 == 0 && (long long)B * (c >> 5) <= 0x7FFFFFFFll && g_pool_variant.load() != 1) {
+        // shared-memory tile, separable box sum (every byte read once)
+        const auto* xs = static_cast<const __nv_bfloat16*>(x_bf16_dev);
+        auto* ys = static_cast<__nv_bfloat16*>(y_bf16_dev);
+        const cudaStream_t st = static_cast<cudaStream_t>(stream);
+        cudaError_t e = k == 2 ? launch_avgpool8<2>(xs, B, c_total, c_off, c, ys, st) : k == 3 ? launch_avgpool8<3>(xs, B, c_total, c_off, c, ys, st)
+                      : k == 4 ? launch_avgpool8<4>(xs, B, c_total, c_off, c, ys, st) : launch_avgpool8<5>(xs, B, c_total, c_off, c, ys, st);
+        if (e != cudaSuccess) { set_error("mups_pool3d: %s", cudaGetErrorString(e)); return MUPS_ERR_CUDA; }
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return MUPS_OK;
+    }
     const int Do = is_max ? D / 2 : D;
     const long long n = (long long)B * Do * Do * Do * (c / 8);
     const int grid = (int)((n + 255) / 256 < 32 * kNumSMs ? (n + 255) / 256 : 32 * kNumSMs);
@@ -394,16 +631,37 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
     if (const char* e = getenv("MUPS_CONV_M_SUB")) a.m_sub = (atoi(e) == 2 && n_tile <= 128) ? 2 : 1;
     const int stage_bytes = a.m_sub * kABytes + n_tile * kTileK * 2;
     int stages = (200 * 1024) / stage_bytes;
+    // short K (the 1^3 layers: 2-24 stages of work per tile): the epilogue is as long as the main loop and nothing overlaps it
+    // inside one CTA, so leave room for TWO CTAs per SM (<= 100 KB of shared memory and 256 TMEM columns each) -- one CTA's
+    // epilogue then runs under the other's loads and MMAs
+    const int iters_total = k * k * k * a.kblocks;
+    if (iters_total <= 24 && m_tiles > kNumSMs && g_conv_variant.load() != 1) stages = (100 * 1024) / stage_bytes < 2 ? 2 : (100 * 1024) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > iters_total) stages = iters_total < 2 ? 2 : iters_total;
     a.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * kMaxStages + 1) * 8 + 16;
+    size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * kMaxStages + 1) * 8 + 16;
+    if (smem < 80 * 1024) smem = 80 * 1024;      // never more than two CTAs per SM: each allocates 256 of the 512 TMEM columns
+
+    // z-halo kernel: 8^3 volumes, k > 1, both accumulators in TMEM (conv_variant 2 forces the per-tap kernel)
+    const bool zhalo = D == 8 && k >= 2 && n_tile <= 128 && g_conv_variant.load() != 2;
+    HaloArgs h{0, 0, 0, 0};
+    if (zhalo) {
+        a.m_sub = 2;
+        h.swap = (n_tile == 128 && g_conv_variant.load() != 3) ? 1 : 0;     // conv_variant 3: z-halo without the operand swap
+        h.a_box_bytes = (4 + k - 1) * 8192;
+        h.na = 2;
+        const int b_bytes = n_tile * kTileK * 2;
+        h.nb = (int)((200 * 1024 - (size_t)h.na * h.a_box_bytes) / b_bytes);
+        if (h.nb > kMaxStages) h.nb = kMaxStages;
+        smem = (size_t)h.na * h.a_box_bytes + (size_t)h.nb * b_bytes + 1024 + (4 + 2 * kMaxStages + 1) * 8 + 16;
+    }
 
     CUtensorMap map_x, map_w;
     {
         const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)B};
         const cuuint64_t strides[4] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cin_total * 2 * D, (cuuint64_t)cin_total * 2 * D * D,
                                        (cuuint64_t)cin_total * 2 * D * D * D};
-        const cuuint32_t box[5] = {(cuuint32_t)kTileK, (cuuint32_t)D, (cuuint32_t)D, (cuuint32_t)a.dz_box, (cuuint32_t)a.b_box};
+        const cuuint32_t box[5] = {(cuuint32_t)kTileK, (cuuint32_t)D, (cuuint32_t)D, (cuuint32_t)(zhalo ? 4 + k - 1 : a.dz_box), (cuuint32_t)a.b_box};
         const cuuint32_t es[5] = {1, 1, 1, 1, 1};
         void* base = const_cast<unsigned char*>(static_cast<const unsigned char*>(x_bf16_dev)) + (size_t)cin_off * 2;
         const CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -419,6 +677,13 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("mups_conv3d_bn_relu: weight tensor map rejected (CUresult %d)", (int)r); return MUPS_ERR_CUDA; }
+    }
+    if (zhalo) {
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_zhalo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv3d_zhalo_kernel<<<dim3((unsigned)(m_tiles / 2), (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+            map_x, map_w, a, h);
+        MUPS_CHECK_LAUNCH();
+        return MUPS_OK;
     }
     MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv3d_tcgen05_kernel<<<dim3((unsigned)((m_tiles + a.m_sub - 1) / a.m_sub), (unsigned)(cout / n_tile)), kConvThreads, smem,

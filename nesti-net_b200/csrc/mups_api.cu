@@ -14,6 +14,8 @@ std::atomic<int64_t> g_launch_count{0};
 std::atomic<int> g_boundary_cap{512};
 std::atomic<int> g_fuse_candidates{3 * 4096};
 std::atomic<int> g_stats_variant{0};
+std::atomic<int> g_pool_variant{0};
+std::atomic<int> g_conv_variant{0};
 std::atomic<int> g_query_kernel{0};
 std::atomic<int> g_query_order{0};
 std::atomic<int> g_hier_margin{-1};
@@ -109,6 +111,11 @@ int mups_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "query_order")) {
         MUPS_REQUIRE(value >= 0 && value <= 2, "mups_set_option: query_order=%lld out of range [0, 2]", (long long)value);
         g_query_order.store((int)value);
+        return MUPS_OK;
+    }
+    if (!strcmp(name, "pool_variant") || !strcmp(name, "conv_variant")) {
+        MUPS_REQUIRE(value >= 0 && value <= (name[0] == 'p' ? 1 : 3), "mups_set_option: %s=%lld out of range", name, (long long)value);
+        (name[0] == 'p' ? g_pool_variant : g_conv_variant).store((int)value);
         return MUPS_OK;
     }
     set_error("mups_set_option: unknown option '%s'", name);

@@ -25,6 +25,8 @@ extern std::atomic<int> g_fuse_candidates;
 extern std::atomic<int> g_stats_variant;
 extern std::atomic<int> g_query_kernel;     // 0 automatic, 1 flat cell scan, 2 hierarchical (octree over the Morton codes)
 extern std::atomic<int> g_hier_margin;      // -1 automatic (6 sqrt(P) + 8); tests set 0 to exercise the worklist hand-over
+extern std::atomic<int> g_pool_variant;     // 0 automatic (shared-memory tile for the 8^3 average pools), 1 per-voxel kernel everywhere
+extern std::atomic<int> g_conv_variant;     // 0 automatic (two CTAs per SM for short-K layers), 1 always one CTA per SM
 extern std::atomic<int> g_query_order;      // 0 automatic, 1 CTAs in caller order, 2 CTAs in Morton order of the centres
 
 #define MUPS_CUDA_TRY(expr)                                                                   \

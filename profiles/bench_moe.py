@@ -43,6 +43,8 @@ def main():
                       "cores": os.cpu_count()}), flush=True)
     net = net.cuda()
     modes = [("gpu fp32 strict", False, None), ("gpu tf32", True, None), ("gpu bf16 autocast", True, torch.bfloat16)]
+    if os.environ.get("ONLY_TC"):            # skip the cuDNN modes (A/B runs of the engine)
+        modes = []
     for name, tf32, amp in modes:
         torch.backends.cudnn.allow_tf32 = tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -85,7 +87,11 @@ def main():
 
     # ---- the hand-written tensor-core engine --------------------------------------------------------------------
     tc = TensorCoreExperts(net)
-    for bsz in sorted({B, int(os.environ.get("B_TC", 1024))}):
+    # TC_VARIANTS="pool,conv;..." : mups_set_option pool_variant / conv_variant pairs to A/B (default: the shipped policy)
+    variants = [tuple(int(v) for v in pair.split(",")) for pair in os.environ.get("TC_VARIANTS", "0,0").split(";")]
+    for pool_v, conv_v, bsz in [(p, c, b) for (p, c) in variants for b in sorted({B, int(os.environ.get("B_TC", 1024))})]:
+        mb._lib.set_option("pool_variant", pool_v)
+        mb._lib.set_option("conv_variant", conv_v)
         qq = np.random.RandomState(1).choice(100000, bsz, replace=False)
         x = mb.mups_features(index, gmm, qq, index.absolute_radii(RADIUS), 512, seed=SEED)
         tc.predict(x)
@@ -101,7 +107,8 @@ def main():
         same = (e_s.cpu() == ref_e)
         rms = float(angular_rms_deg(n_s.float().cpu()[same], ref_n[same])) if bool(same.any()) else None
         flops = 6.0e10 * bsz
-        print(json.dumps({"mode": "tcgen05 engine (bf16 x bf16 -> fp32 in TMEM)", "batch": bsz, "ms_per_batch": round(ms, 2),
+        print(json.dumps({"mode": "tcgen05 engine (bf16 x bf16 -> fp32 in TMEM)", "pool_variant": pool_v, "conv_variant": conv_v,
+                          "batch": bsz, "ms_per_batch": round(ms, 2),
                           "queries_per_s": round(bsz / ms * 1e3, 1), "approx_TFLOPs": round(flops / ms / 1e9, 1),
                           "normals_rms_deg_vs_host_fp32": rms, "same_expert": "%d/%d" % (int(same.sum()), n_ref)}), flush=True)
 

@@ -928,7 +928,9 @@ def _conv_reference(x, cin_off, cin, w, scale, shift, relu, k):
 @pytest.mark.parametrize("D,k,ct,cin_off,cin,cout,B", [
     (8, 1, 128, 0, 128, 128, 3), (8, 3, 128, 0, 128, 64, 2), (8, 5, 64, 0, 64, 64, 2), (8, 3, 128, 32, 32, 32, 2),
     (8, 5, 256, 0, 256, 128, 1), (4, 2, 768, 0, 768, 256, 5), (4, 4, 512, 0, 512, 256, 3), (2, 2, 512, 0, 512, 256, 37),
-    (2, 1, 1536, 0, 1536, 512, 20), (1, 1, 1536, 0, 1536, 1024, 300), (1, 1, 128, 0, 128, 16, 130), (8, 3, 96, 0, 96, 16, 1)])
+    (2, 1, 1536, 0, 1536, 512, 20), (1, 1, 1536, 0, 1536, 1024, 300), (1, 1, 128, 0, 128, 16, 130), (8, 3, 96, 0, 96, 16, 1),
+    (8, 2, 64, 0, 64, 32, 3), (8, 4, 128, 64, 64, 48, 2), (8, 5, 384, 0, 384, 256, 2), (8, 1, 384, 0, 384, 256, 40),
+    (8, 3, 256, 0, 256, 128, 3), (8, 5, 136, 8, 128, 128, 2)])
 def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     """mups_conv3d_bn_relu (tcgen05 / TMEM / TMA implicit GEMM, csrc/moe_conv.cu) against torch conv3d in fp32 on the same
     bf16-rounded operands: every volume edge and kernel edge of the reference's networks, 'SAME' padding for even kernels,
@@ -953,12 +955,28 @@ def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     got = out.reshape(-1, cout + 16)
     assert torch.all(got[:, :8] == 7.0) and torch.all(got[:, 8 + cout:] == 7.0), "wrote outside its channel slice"
     assert torch.equal(got[:, 8:8 + cout], f32.to(torch.bfloat16)), "bf16 output is not the rounded fp32 output"
+    if D == 8 and k > 1 and cout <= 128:
+        # the default above was the z-halo kernel (one activation box per (dy, dx, channel block) serves all dz taps);
+        # conv_variant 2 forces the per-tap kernel: same products, another summation order
+        # (cout = 128: with the operand roles swapped, one N = 256 MMA over both voxel tiles; conv_variant 3 = unswapped)
+        for variant in (2, 3):
+            _lib.set_option("conv_variant", variant)
+            try:
+                f32b = torch.empty_like(f32)
+                me.conv3d_bn_relu(x, cin_off, cin, layer, None, 0, f32b)
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_option("conv_variant", 0)
+            assert (f32b - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+            assert (f32b - f32).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("D,k,is_max", [(8, 3, False), (4, 2, False), (8, 2, False), (8, 2, True), (4, 2, True), (2, 2, True)])
+@pytest.mark.parametrize("D,k,is_max", [(8, 3, False), (4, 2, False), (8, 2, False), (8, 4, False), (8, 5, False), (4, 3, False),
+                                        (8, 2, True), (4, 2, True), (2, 2, True)])
 def test_pool3d_against_tf_semantics(D, k, is_max):
     """mups_pool3d against experts_net.avg_pool_same / max_pool_same (TF 'SAME': the average counts only valid cells) on a
-    channel slice of a bf16 NDHWC tensor."""
+    channel slice of a bf16 NDHWC tensor; the 8^3 average pools run the shared-memory tile kernel (separable box sum) and
+    are also compared with the per-voxel kernel (pool_variant 1)."""
     from nesti_net_b200 import moe_engine as me
     from nesti_net_b200.experts_net import avg_pool_same, max_pool_same
     torch.manual_seed(D + k)
@@ -968,6 +986,17 @@ def test_pool3d_against_tf_semantics(D, k, is_max):
     ref = (max_pool_same(v, 2, 2) if is_max else avg_pool_same(v, k)).permute(0, 2, 3, 4, 1)
     assert tuple(got.shape) == tuple(ref.shape)
     assert torch.equal(got, ref.to(torch.bfloat16)) if is_max else (got.float() - ref).abs().max().item() < 2e-2
+    if not is_max and D == 8:
+        _lib.set_option("pool_variant", 1)
+        try:
+            plain = me.pool3d(x, 16, 64, k, is_max)
+        finally:
+            _lib.set_option("pool_variant", 0)
+        # same fp32 sums in another order: at most one bf16 rounding step apart
+        assert ((got.float() - plain.float()).abs() <= 2.0 ** -7 * plain.float().abs() + 1e-6).all()
+        odd = me.pool3d(x, 8, 24, k, is_max)               # 24 channels: not a multiple of 32 -> per-voxel kernel
+        ref24 = avg_pool_same(x[..., 8:32].float().permute(0, 4, 1, 2, 3), k).permute(0, 2, 3, 4, 1)
+        assert (odd.float() - ref24).abs().max().item() < 2e-2
 
 
 def test_tensor_core_consumer_against_fp32_network():
