@@ -338,7 +338,7 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 tma_load_5d(smem_u32(smem + (size_t)sa * h.a_box_bytes), &map_x, bar_afull + 8 * sa, kb * kTileK, dx - a.pl, dy - a.pl,
                             tz0[0] - a.pl, tb0[0]);
                 if (++sa == h.na) { sa = 0; pa ^= 1; }
-                for (int dz = 0; dz < a.k; ++dz) {
+                for (int i = 0, dz = a.pl; i < a.k; ++i, dz = dz + 1 == a.k ? 0 : dz + 1) {    // dz = pl first (see the MMA loop)
                     mbar_wait(bar_bempty + 8 * sb, pb);
                     mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_bytes);
                     tma_load_3d(smem_u32(smem_b + (size_t)sb * b_bytes), &map_w, bar_bfull + 8 * sb, kb * kTileK, n0, (dz * a.k + dy) * a.k + dx);
@@ -354,7 +354,9 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         for (int st = 0; st < steps; ++st) {
             mbar_wait(bar_afull + 8 * sa, pa);
             const uint32_t abase = smem_u32(smem + (size_t)sa * h.a_box_bytes);
-            for (int dz = 0; dz < a.k; ++dz) {
+            // taps in the order dz = pl, pl + 1, ..., k - 1, 0, ..., pl - 1: the first one reads only in-volume slices, so it
+            // initialises every accumulator column and the later taps may skip their out-of-volume slices
+            for (int i = 0, dz = a.pl; i < a.k; ++i, dz = dz + 1 == a.k ? 0 : dz + 1) {
                 mbar_wait(bar_bfull + 8 * sb, pb);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
@@ -363,20 +365,24 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         // D^T[128 channels x 256 voxels] += W[128 x 64] * X[256 x 64]^T: ONE N = 256 MMA per K step covers both
                         // voxel tiles (box slices dz .. dz + 3 are 256 contiguous rows): 12 KB of operand reads per 128
                         // tensor cycles instead of 16 KB for two N = 128 MMAs
-                        const uint64_t dxv = umma_desc(abase + (uint32_t)dz * 8192u);
+                        // box slice s holds input slice z0 - pl + s; tap dz reads s in [dz, dz + 4): the slices outside the
+                        // volume are zeros -- leave them (whole 64-voxel column groups) out of the MMA: 15 % of the work at k = 5
+                        const int lo = max(dz, a.pl - tz0[0]), hi = min(dz + 4, a.D + a.pl - tz0[0]);
+                        const uint64_t dxv = umma_desc(abase + (uint32_t)lo * 8192u);
+                        const uint32_t idesc_n = (idesc_swapped & ~(0x3Fu << 17)) | ((uint32_t)((hi - lo) * 64 >> 3) << 17);
 #pragma unroll
                         for (int k = 0; k < kTileK / 16; ++k)
-                            umma_bf16(tmem_base, db + 2 * k, dxv + 2 * k, idesc_swapped, (st > 0 || dz > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tmem_base + (uint32_t)((lo - dz) * 64), db + 2 * k, dxv + 2 * k, idesc_n, (st > 0 || i > 0 || k > 0) ? 1u : 0u);
                     } else
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {            // tile u = slices 2u, 2u + 1 of the CTA; tap dz reads box slices 2u + dz, +1
                         const uint64_t da = umma_desc(abase + (uint32_t)(2 * u + dz) * 8192u);
 #pragma unroll
                         for (int k = 0; k < kTileK / 16; ++k)
-                            umma_bf16(tmem_base + (uint32_t)(u * a.n_tile), da + 2 * k, db + 2 * k, idesc, (st > 0 || dz > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tmem_base + (uint32_t)(u * a.n_tile), da + 2 * k, db + 2 * k, idesc, (st > 0 || i > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(bar_bempty + 8 * sb);
-                    if (dz == a.k - 1) {
+                    if (i == a.k - 1) {
                         umma_commit(bar_aempty + 8 * sa);    // the box is free once the MMAs of its last tap have read it
                         if (st == steps - 1) umma_commit(bar_acc);
                     }
