@@ -263,7 +263,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 // slices = two 128-voxel tiles, plus the halo; out-of-volume slices / rows / columns zero-filled by the TMA unit) and issues
 // the MMAs of all k dz-taps of both tiles from it, the descriptor start advanced by (2 u + dz) * 8 KB.  Activation traffic per
 // tap falls from 32 KB to (4 + k - 1) * 8 / k KB (12.8 KB at k = 5); the weights stream through their own ring.
-struct HaloArgs { int na, nb, a_box_bytes, swap; };   // A stages, B stages, bytes of one activation box, operand roles swapped
+struct HaloArgs { int na, nb, a_box_bytes, swap, ext; };   // A stages, B stages, bytes of one activation box, operand roles swapped, z-slices per box
 
 // Epilogue of the z-halo kernel with SWAPPED operand roles (accumulator = [128 output channels (TMEM lanes)] x [256 voxels
 // (columns)]): a thread owns one output channel, a warp's store covers 32 consecutive channels of one voxel (64 bytes).
@@ -297,10 +297,10 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = a.n_tile * kTileK * 2;
     unsigned char* smem_b = smem + (size_t)h.na * h.a_box_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)h.nb * b_bytes);   // a_full[2], a_empty[2], b_full[8], b_empty[8], accumulator
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kMaxStages + 1);
-    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 2), bar_bfull = smem_u32(bars + 4),
-                   bar_bempty = smem_u32(bars + 4 + kMaxStages), bar_acc = smem_u32(bars + 4 + 2 * kMaxStages);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)h.nb * b_bytes);   // a_full[4], a_empty[4], b_full[8], b_empty[8], accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMaxStages + 1);
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 4), bar_bfull = smem_u32(bars + 8),
+                   bar_bempty = smem_u32(bars + 8 + kMaxStages), bar_acc = smem_u32(bars + 8 + 2 * kMaxStages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -308,7 +308,7 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -328,6 +328,13 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int tb0[2] = {(int)(blockIdx.x >> 1), (int)(blockIdx.x >> 1)};
     const int tz0[2] = {(int)(blockIdx.x & 1) * 4, (int)(blockIdx.x & 1) * 4 + 2};
     const int steps = a.kblocks * a.k * a.k;            // (64-channel block, dy, dx)
+    // the box: h.ext z-slices starting at input slice z_box.  Untrimmed (ext = 4 + k - 1): z_box = z0 - pl, the out-of-volume
+    // slices are zero-filled.  Trimmed (swapped path, whose MMAs never read an out-of-volume slice): only the in-volume slices
+    // this half of the sample can reach -- [0, ext) for the lower half, [8 - ext, 8) for the upper -- 48 instead of 64 KB at
+    // k = 5, which buys a third box in the ring.  Logical slice s (input slice z0 - pl + s) lies at box slice s + soff.
+    const bool trimmed = h.ext < 4 + a.k - 1;
+    const int z_box = trimmed ? (tz0[0] == 0 ? 0 : a.D - h.ext) : tz0[0] - a.pl;
+    const int soff = tz0[0] - a.pl - z_box;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -336,7 +343,7 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 mbar_wait(bar_aempty + 8 * sa, pa);
                 mbar_expect_tx(bar_afull + 8 * sa, (uint32_t)h.a_box_bytes);
                 tma_load_5d(smem_u32(smem + (size_t)sa * h.a_box_bytes), &map_x, bar_afull + 8 * sa, kb * kTileK, dx - a.pl, dy - a.pl,
-                            tz0[0] - a.pl, tb0[0]);
+                            z_box, tb0[0]);
                 if (++sa == h.na) { sa = 0; pa ^= 1; }
                 for (int i = 0, dz = a.pl; i < a.k; ++i, dz = dz + 1 == a.k ? 0 : dz + 1) {    // dz = pl first (see the MMA loop)
                     mbar_wait(bar_bempty + 8 * sb, pb);
@@ -368,7 +375,7 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         // box slice s holds input slice z0 - pl + s; tap dz reads s in [dz, dz + 4): the slices outside the
                         // volume are zeros -- leave them (whole 64-voxel column groups) out of the MMA: 15 % of the work at k = 5
                         const int lo = max(dz, a.pl - tz0[0]), hi = min(dz + 4, a.D + a.pl - tz0[0]);
-                        const uint64_t dxv = umma_desc(abase + (uint32_t)lo * 8192u);
+                        const uint64_t dxv = umma_desc(abase + (uint32_t)(lo + soff) * 8192u);
                         const uint32_t idesc_n = (idesc_swapped & ~(0x3Fu << 17)) | ((uint32_t)((hi - lo) * 64 >> 3) << 17);
 #pragma unroll
                         for (int k = 0; k < kTileK / 16; ++k)
@@ -376,7 +383,7 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     } else
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {            // tile u = slices 2u, 2u + 1 of the CTA; tap dz reads box slices 2u + dz, +1
-                        const uint64_t da = umma_desc(abase + (uint32_t)(2 * u + dz) * 8192u);
+                        const uint64_t da = umma_desc(abase + (uint32_t)(2 * u + dz + soff) * 8192u);
 #pragma unroll
                         for (int k = 0; k < kTileK / 16; ++k)
                             umma_bf16(tmem_base + (uint32_t)(u * a.n_tile), da + 2 * k, db + 2 * k, idesc, (st > 0 || i > 0 || k > 0) ? 1u : 0u);
@@ -480,10 +487,16 @@ __global__ void __launch_bounds__(256) avgpool8_tile_kernel(const __nv_bfloat16*
     const int chunk = blockIdx.x % chunks;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const __nv_bfloat16* src = x + b * 512 * (long long)ct + c_off + chunk * 32;
-    for (int i = tid; i < 512 * 4; i += 256) {                     // 16-byte loads: 4 per voxel
-        const int v = i >> 2, part = i & 3;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + v * (long long)ct) + part);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    uint4 raw[8];                                                  // 16-byte loads, 4 per voxel: all eight in flight at once
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = tid + r * 256;
+        raw[r] = __ldg(reinterpret_cast<const uint4*>(src + (i >> 2) * (long long)ct) + (i & 3));
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = tid + r * 256, v = i >> 2, part = i & 3;
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[r]);
         const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
         float4* dst = reinterpret_cast<float4*>(tile + v * 32 + part * 8);
         dst[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
@@ -541,6 +554,33 @@ static cudaError_t launch_avgpool8(const __nv_bfloat16* x, long long B, int ct, 
     return cudaGetLastError();
 }
 
+// tf.nn.max_pool3d(2, stride 2) on NDHWC bf16 (utils/tf_util.py:406-430; D even, so 'SAME' needs no padding): one thread per
+// (output voxel, 8-channel chunk), the eight 16-byte loads of its window issued back to back, 32-bit index arithmetic.
+__global__ void __launch_bounds__(256) maxpool2_kernel(const __nv_bfloat16* __restrict__ x, unsigned n, int D, int ct, int c_off, int c,
+                                                       __nv_bfloat16* __restrict__ y) {
+    const unsigned chunks = (unsigned)c >> 3, Do = (unsigned)D >> 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned ch = i % chunks, v = i / chunks;
+        const unsigned xo = v % Do, yo = (v / Do) % Do, zo = (v / (Do * Do)) % Do, b = v / (Do * Do * Do);
+        const size_t vin = (((size_t)b * D + 2 * zo) * D + 2 * yo) * D + 2 * xo;
+        const uint4* p = reinterpret_cast<const uint4*>(x + vin * ct + c_off) + ch;
+        const size_t sx = (size_t)ct / 8, sy = sx * D, sz = sy * D;            // strides in 16-byte units
+        uint4 r[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) r[t] = __ldg(p + (t & 1) * sx + ((t >> 1) & 1) * sy + (t >> 2) * sz);
+        uint4 out;
+        __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 m = reinterpret_cast<const __nv_bfloat162*>(&r[0])[j];
+#pragma unroll
+            for (int t = 1; t < 8; ++t) m = __hmax2(m, reinterpret_cast<const __nv_bfloat162*>(&r[t])[j]);
+            o[j] = m;
+        }
+        reinterpret_cast<uint4*>(y + (size_t)v * c)[ch] = out;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -589,6 +629,14 @@ int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off
                       : k == 4 ? launch_avgpool8<4>(xs, B, c_total, c_off, c, ys, st) : launch_avgpool8<5>(xs, B, c_total, c_off, c, ys, st);
         if (e != cudaSuccess) { set_error("mups_pool3d: %s", cudaGetErrorString(e)); return MUPS_ERR_CUDA; }
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return MUPS_OK;
+    }
+    if (is_max && (long long)B * D * D * D * (c_total / 8) < 0xFFFFFFFFll && g_pool_variant.load() != 1) {
+        const unsigned n = (unsigned)((long long)B * (D / 2) * (D / 2) * (D / 2) * (c / 8));
+        const unsigned grid = (n + 255) / 256;
+        maxpool2_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16_dev), n, D, c_total, c_off, c,
+                                                                               static_cast<__nv_bfloat16*>(y_bf16_dev));
+        MUPS_CHECK_LAUNCH();
         return MUPS_OK;
     }
     const int Do = is_max ? D / 2 : D;
@@ -650,16 +698,17 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
 
     // z-halo kernel: 8^3 volumes, k > 1, both accumulators in TMEM (conv_variant 2 forces the per-tap kernel)
     const bool zhalo = D == 8 && k >= 2 && n_tile <= 128 && g_conv_variant.load() != 2;
-    HaloArgs h{0, 0, 0, 0};
+    HaloArgs h{0, 0, 0, 0, 0};
     if (zhalo) {
         a.m_sub = 2;
         h.swap = (n_tile == 128 && g_conv_variant.load() != 3) ? 1 : 0;     // conv_variant 3: z-halo without the operand swap
-        h.a_box_bytes = (4 + k - 1) * 8192;
-        h.na = 2;
+        h.ext = h.swap ? 4 + (k - 1 - a.pl) : 4 + k - 1;                    // swapped path: in-volume slices only (see the kernel)
+        h.a_box_bytes = h.ext * 8192;
         const int b_bytes = n_tile * kTileK * 2;
+        h.na = (3 * (size_t)h.a_box_bytes + 3 * (size_t)b_bytes <= 200 * 1024) ? 3 : 2;
         h.nb = (int)((200 * 1024 - (size_t)h.na * h.a_box_bytes) / b_bytes);
         if (h.nb > kMaxStages) h.nb = kMaxStages;
-        smem = (size_t)h.na * h.a_box_bytes + (size_t)h.nb * b_bytes + 1024 + (4 + 2 * kMaxStages + 1) * 8 + 16;
+        smem = (size_t)h.na * h.a_box_bytes + (size_t)h.nb * b_bytes + 1024 + (8 + 2 * kMaxStages + 1) * 8 + 16;
     }
 
     CUtensorMap map_x, map_w;
@@ -667,7 +716,7 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
         const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)D, (cuuint64_t)B};
         const cuuint64_t strides[4] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cin_total * 2 * D, (cuuint64_t)cin_total * 2 * D * D,
                                        (cuuint64_t)cin_total * 2 * D * D * D};
-        const cuuint32_t box[5] = {(cuuint32_t)kTileK, (cuuint32_t)D, (cuuint32_t)D, (cuuint32_t)(zhalo ? 4 + k - 1 : a.dz_box), (cuuint32_t)a.b_box};
+        const cuuint32_t box[5] = {(cuuint32_t)kTileK, (cuuint32_t)D, (cuuint32_t)D, (cuuint32_t)(zhalo ? h.ext : a.dz_box), (cuuint32_t)a.b_box};
         const cuuint32_t es[5] = {1, 1, 1, 1, 1};
         void* base = const_cast<unsigned char*>(static_cast<const unsigned char*>(x_bf16_dev)) + (size_t)cin_off * 2;
         const CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
