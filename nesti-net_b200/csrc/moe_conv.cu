@@ -705,8 +705,11 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
         h.ext = h.swap ? 4 + (k - 1 - a.pl) : 4 + k - 1;                    // swapped path: in-volume slices only (see the kernel)
         h.a_box_bytes = h.ext * 8192;
         const int b_bytes = n_tile * kTileK * 2;
-        h.na = (3 * (size_t)h.a_box_bytes + 3 * (size_t)b_bytes <= 200 * 1024) ? 3 : 2;
-        h.nb = (int)((200 * 1024 - (size_t)h.na * h.a_box_bytes) / b_bytes);
+        const size_t budget = 224 * 1024;                                   // of the 227 KB a CTA may have
+        h.na = (3 * (size_t)h.a_box_bytes + 4 * (size_t)b_bytes <= budget) ? 3 : 2;
+        if (const char* e = getenv("MUPS_CONV_NA")) h.na = atoi(e) == 3 ? 3 : 2;       // benchmarking override
+        h.nb = (int)((budget - (size_t)h.na * h.a_box_bytes) / b_bytes);
+        if (const char* e = getenv("MUPS_CONV_NB")) h.nb = atoi(e) < h.nb ? (atoi(e) < 2 ? 2 : atoi(e)) : h.nb;
         if (h.nb > kMaxStages) h.nb = kMaxStages;
         smem = (size_t)h.na * h.a_box_bytes + (size_t)h.nb * b_bytes + 1024 + (8 + 2 * kMaxStages + 1) * 8 + 16;
     }
