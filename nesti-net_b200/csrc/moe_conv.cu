@@ -263,12 +263,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 // slices = two 128-voxel tiles, plus the halo; out-of-volume slices / rows / columns zero-filled by the TMA unit) and issues
 // the MMAs of all k dz-taps of both tiles from it, the descriptor start advanced by (2 u + dz) * 8 KB.  Activation traffic per
 // tap falls from 32 KB to (4 + k - 1) * 8 / k KB (12.8 KB at k = 5); the weights stream through their own ring.
-struct HaloArgs { int na, nb, a_box_bytes, swap, ext; };   // A stages, B stages, bytes of one activation box, operand roles swapped, z-slices per box
+struct HaloArgs { int na, nb, a_box_bytes, swap, ext, nz; };   // A stages, B stages, bytes of one activation box, operand roles swapped,
+                                                                 // z-slices per box, output z-slices per CTA (4, or 8 = the whole sample)
 
 // Epilogue of the z-halo kernel with SWAPPED operand roles (accumulator = [128 output channels (TMEM lanes)] x [256 voxels
 // (columns)]): a thread owns one output channel, a warp's store covers 32 consecutive channels of one voxel (64 bytes).
 __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_t bar_acc, uint32_t tmem_base, int warp, int lane, int n0,
-                                                      long long voxel0) {
+                                                      long long voxel0, int voxels) {
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;
@@ -277,7 +278,7 @@ __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_
     const float sc = real ? __ldg(a.scale + co) : 0.f, sh = real ? __ldg(a.shift + co) : 0.f;
     __nv_bfloat16* ycol = a.y ? a.y + voxel0 * a.y_stride + a.cout_off + co : nullptr;
     float* fcol = a.y_f32 ? a.y_f32 + voxel0 * (long long)a.Cout + co : nullptr;
-    for (int j0 = 0; j0 < 256; j0 += 16) {
+    for (int j0 = 0; j0 < voxels; j0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)j0, v);
 #pragma unroll
@@ -302,6 +303,7 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + 4), bar_bfull = smem_u32(bars + 8),
                    bar_bempty = smem_u32(bars + 8 + kMaxStages), bar_acc = smem_u32(bars + 8 + 2 * kMaxStages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = h.nz == 8 ? 512u : (uint32_t)kTmemCols;      // whole sample: two 256-column accumulators
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -314,7 +316,7 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -324,15 +326,18 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     // this CTA: sample blockIdx.x / 2, z-slices [4 (blockIdx.x & 1), +4) = tiles 2 blockIdx.x, 2 blockIdx.x + 1; n_tile channels at n0
     const int n0 = blockIdx.y * a.n_tile;
-    const int tile0 = blockIdx.x * 2;
-    const int tb0[2] = {(int)(blockIdx.x >> 1), (int)(blockIdx.x >> 1)};
-    const int tz0[2] = {(int)(blockIdx.x & 1) * 4, (int)(blockIdx.x & 1) * 4 + 2};
+    // (whole-sample mode, h.nz == 8: sample blockIdx.x, all eight slices -- every weight tile then serves 512 voxels)
+    const int tile0 = h.nz == 8 ? blockIdx.x * 4 : blockIdx.x * 2;
+    const int sample = h.nz == 8 ? (int)blockIdx.x : (int)(blockIdx.x >> 1);
+    const int zfirst = h.nz == 8 ? 0 : (int)(blockIdx.x & 1) * 4;
+    const int tb0[2] = {sample, sample};
+    const int tz0[2] = {zfirst, zfirst + 2};
     const int steps = a.kblocks * a.k * a.k;            // (64-channel block, dy, dx)
     // the box: h.ext z-slices starting at input slice z_box.  Untrimmed (ext = 4 + k - 1): z_box = z0 - pl, the out-of-volume
     // slices are zero-filled.  Trimmed (swapped path, whose MMAs never read an out-of-volume slice): only the in-volume slices
     // this half of the sample can reach -- [0, ext) for the lower half, [8 - ext, 8) for the upper -- 48 instead of 64 KB at
     // k = 5, which buys a third box in the ring.  Logical slice s (input slice z0 - pl + s) lies at box slice s + soff.
-    const bool trimmed = h.ext < 4 + a.k - 1;
+    const bool trimmed = h.ext < h.nz + a.k - 1;
     const int z_box = trimmed ? (tz0[0] == 0 ? 0 : a.D - h.ext) : tz0[0] - a.pl;
     const int soff = tz0[0] - a.pl - z_box;
 
@@ -374,12 +379,15 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         // tensor cycles instead of 16 KB for two N = 128 MMAs
                         // box slice s holds input slice z0 - pl + s; tap dz reads s in [dz, dz + 4): the slices outside the
                         // volume are zeros -- leave them (whole 64-voxel column groups) out of the MMA: 15 % of the work at k = 5
-                        const int lo = max(dz, a.pl - tz0[0]), hi = min(dz + 4, a.D + a.pl - tz0[0]);
-                        const uint64_t dxv = umma_desc(abase + (uint32_t)(lo + soff) * 8192u);
-                        const uint32_t idesc_n = (idesc_swapped & ~(0x3Fu << 17)) | ((uint32_t)((hi - lo) * 64 >> 3) << 17);
+                        for (int half = 0; half < (h.nz >> 2); ++half) {       // one N <= 256 MMA per group of four output slices
+                            const int lo = max(dz + 4 * half, a.pl - tz0[0]), hi = min(dz + 4 * half + 4, a.D + a.pl - tz0[0]);
+                            if (hi <= lo) continue;
+                            const uint64_t dxv = umma_desc(abase + (uint32_t)(lo + soff) * 8192u);
+                            const uint32_t idesc_n = (idesc_swapped & ~(0x3Fu << 17)) | ((uint32_t)((hi - lo) * 64 >> 3) << 17);
 #pragma unroll
-                        for (int k = 0; k < kTileK / 16; ++k)
-                            umma_bf16(tmem_base + (uint32_t)((lo - dz) * 64), db + 2 * k, dxv + 2 * k, idesc_n, (st > 0 || i > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kTileK / 16; ++k)
+                                umma_bf16(tmem_base + (uint32_t)((lo - dz) * 64), db + 2 * k, dxv + 2 * k, idesc_n, (st > 0 || i > 0 || k > 0) ? 1u : 0u);
+                        }
                     } else
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {            // tile u = slices 2u, 2u + 1 of the CTA; tap dz reads box slices 2u + dz, +1
@@ -400,14 +408,14 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             if (++sa == h.na) { sa = 0; pa ^= 1; }
         }
     } else if (h.swap) {
-        conv_epilogue_swapped(a, bar_acc, tmem_base, warp, lane, n0, (long long)tb0[0] * 512 + tz0[0] * 64);
+        conv_epilogue_swapped(a, bar_acc, tmem_base, warp, lane, n0, (long long)tb0[0] * 512 + tz0[0] * 64, h.nz * 64);
     } else {
         conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
     }
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -698,11 +706,14 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
 
     // z-halo kernel: 8^3 volumes, k > 1, both accumulators in TMEM (conv_variant 2 forces the per-tap kernel)
     const bool zhalo = D == 8 && k >= 2 && n_tile <= 128 && g_conv_variant.load() != 2;
-    HaloArgs h{0, 0, 0, 0, 0};
+    HaloArgs h{0, 0, 0, 0, 0, 4};
     if (zhalo) {
         a.m_sub = 2;
         h.swap = (n_tile == 128 && g_conv_variant.load() != 3) ? 1 : 0;     // conv_variant 3: z-halo without the operand swap
-        h.ext = h.swap ? 4 + (k - 1 - a.pl) : 4 + k - 1;                    // swapped path: in-volume slices only (see the kernel)
+        // whole sample per CTA (weights read once per 512 voxels: L2 -> SM traffic -40 %) when the batch still fills the
+        // machine four times over; conv_variant 4 forces the half-sample CTAs
+        h.nz = (h.swap && B >= 4 * kNumSMs && g_conv_variant.load() != 4) ? 8 : 4;
+        h.ext = h.nz == 8 ? 8 : h.swap ? 4 + (k - 1 - a.pl) : 4 + k - 1;    // swapped path: in-volume slices only (see the kernel)
         h.a_box_bytes = h.ext * 8192;
         const int b_bytes = n_tile * kTileK * 2;
         const size_t budget = 224 * 1024;                                   // of the 227 KB a CTA may have
@@ -738,7 +749,7 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
     }
     if (zhalo) {
         MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_zhalo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv3d_zhalo_kernel<<<dim3((unsigned)(m_tiles / 2), (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        conv3d_zhalo_kernel<<<dim3((unsigned)(h.nz == 8 ? m_tiles / 4 : m_tiles / 2), (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(
             map_x, map_w, a, h);
         MUPS_CHECK_LAUNCH();
         return MUPS_OK;

@@ -930,7 +930,8 @@ def _conv_reference(x, cin_off, cin, w, scale, shift, relu, k):
     (8, 5, 256, 0, 256, 128, 1), (4, 2, 768, 0, 768, 256, 5), (4, 4, 512, 0, 512, 256, 3), (2, 2, 512, 0, 512, 256, 37),
     (2, 1, 1536, 0, 1536, 512, 20), (1, 1, 1536, 0, 1536, 1024, 300), (1, 1, 128, 0, 128, 16, 130), (8, 3, 96, 0, 96, 16, 1),
     (8, 2, 64, 0, 64, 32, 3), (8, 4, 128, 64, 64, 48, 2), (8, 5, 384, 0, 384, 256, 2), (8, 1, 384, 0, 384, 256, 40),
-    (8, 3, 256, 0, 256, 128, 3), (8, 5, 136, 8, 128, 128, 2)])
+    (8, 3, 256, 0, 256, 128, 3), (8, 5, 136, 8, 128, 128, 2),
+    (8, 3, 128, 0, 128, 128, 600), (8, 4, 64, 0, 64, 128, 593)])
 def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     """mups_conv3d_bn_relu (tcgen05 / TMEM / TMA implicit GEMM, csrc/moe_conv.cu) against torch conv3d in fp32 on the same
     bf16-rounded operands: every volume edge and kernel edge of the reference's networks, 'SAME' padding for even kernels,
@@ -959,7 +960,8 @@ def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
         # the default above was the z-halo kernel (one activation box per (dy, dx, channel block) serves all dz taps);
         # conv_variant 2 forces the per-tap kernel: same products, another summation order
         # (cout = 128: with the operand roles swapped, one N = 256 MMA over both voxel tiles; conv_variant 3 = unswapped)
-        for variant in (2, 3):
+        # (batches >= 592: one CTA per whole sample, two N = 256 accumulators; conv_variant 4 = half-sample CTAs)
+        for variant in (2, 3, 4):
             _lib.set_option("conv_variant", variant)
             try:
                 f32b = torch.empty_like(f32)
