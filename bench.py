@@ -730,7 +730,7 @@ def run_clouds(args, cfg):
         torch.manual_seed(1234)
         tc = TensorCoreExperts(ExpertsNormalEstimator(n_rads=S, n_gaussians=G, n_experts=7).eval().to(dev))
         nq_n = int(os.environ.get("MUPS_BENCH_NORMALS_QUERIES", "16384"))
-        pipe_n = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=1024)
+        pipe_n = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=2048)
         normals_host = torch.empty((nq_n, 3), dtype=torch.float32).pin_memory()
         qn_host = (torch.arange(nq_n, dtype=torch.int64) * (N_POINTS // nq_n)).pin_memory()
 
@@ -748,7 +748,7 @@ def run_clouds(args, cfg):
                           "d2h_bytes_per_step": n_n * 12, "chunk_queries": pipe_n.chunk, "finite": bool(torch.isfinite(normals_host).all()),
                           "api": "host cloud in -> MuPSPipeline.features_to_consumer -> moe_engine.TensorCoreExperts.predict (tcgen05 conv3d, "
                                  "bf16 x bf16 -> fp32) -> normals to pinned host memory; random-init 7-expert network, one GPU",
-                          "cudnn_strict_fp32_queries_per_s": 773, "cudnn_source": "profiles/r02_moe.jsonl"}
+                          "cudnn_strict_fp32_queries_per_s": 774, "cudnn_source": "profiles/r02_moe.jsonl"}
         del tc, pipe_n
 
     cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",

@@ -20,6 +20,7 @@
 // Both end with the same epilogue: masked-slot zeros, scale factors, /n_eff, signed square root,
 // per-channel L2 norm over the Gaussians (CTA-wide reduction), direct store into
 // [B, res, res, res, 20*S] (or channel-major).
+#include <cstdlib>
 #include <cooperative_groups.h>
 
 #include "mups_common.cuh"
@@ -909,8 +910,12 @@ int launch_3dmfv(const mups_gmm* gmm, const float* patches, const int32_t* n_eff
         const int TPP = kSepTilePoints / 2;
         const bool serial = log_res <= 3 && variant != 1;
         const int pitch = a.res[0] + (serial ? 1 : 0);
-        const size_t smem = (size_t)TPP * 3 * pitch * (sizeof(float4) + sizeof(float2)) +
-                            sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
+        size_t smem = (size_t)TPP * 3 * pitch * (sizeof(float4) + sizeof(float2)) +
+                      sizeof(float) * (3 * 64 + (kSepThreads / 32) * 20 + 32 + 3 * (size_t)a.P);
+        // experiment knob (profiles/README.md): extra dynamic shared memory lowers the CTAs per SM of this kernel so that a
+        // ball-query CTA of the next cloud can co-reside on the side stream
+        static const int smem_pad = getenv("MUPS_STATS_SMEM_PAD") ? atoi(getenv("MUPS_STATS_SMEM_PAD")) : 0;
+        if (smem_pad > 0 && smem + smem_pad <= 200 * 1024) smem += smem_pad;
 #define MUPS_LAUNCH_SEP(MODE, LOG, STG)                                                                             \
     do {                                                                                                            \
         MUPS_CUDA_TRY(cudaFuncSetAttribute(stats_separable_kernel<MODE, LOG, 1, STG>,                               \
