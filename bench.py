@@ -729,27 +729,26 @@ def run_clouds(args, cfg):
         from nesti_net_b200.moe_engine import TensorCoreExperts
         torch.manual_seed(1234)
         tc = TensorCoreExperts(ExpertsNormalEstimator(n_rads=S, n_gaussians=G, n_experts=7).eval().to(dev))
+        from nesti_net_b200.inference import CloudNormalEstimator
         nq_n = int(os.environ.get("MUPS_BENCH_NORMALS_QUERIES", "16384"))
-        pipe_n = mb.MuPSPipeline(gmm, RADIUS, P, seed=SEED, chunk=2048)
-        normals_host = torch.empty((nq_n, 3), dtype=torch.float32).pin_memory()
+        est = CloudNormalEstimator(tc, gmm, RADIUS, P, seed=SEED, chunk=2048)
+        pipe_n = est.pipe
         qn_host = (torch.arange(nq_n, dtype=torch.int64) * (N_POINTS // nq_n)).pin_memory()
-
-        def to_normals(lo_, hi_, rows_):
-            nrm, _, _ = tc.predict(rows_.view(hi_ - lo_, RES, RES, RES, 20 * S))
-            normals_host[lo_:hi_].copy_(nrm, non_blocking=True)
-        pipe_n.features_to_consumer(hosts[0], qn_host[:2048], to_normals)
+        est(hosts[0], qn_host[:2048])                                   # warm-up (allocations, tensor maps)
         torch.cuda.synchronize()
         pipe_n.h2d_bytes = 0
         w0 = time.perf_counter()
-        n_n = pipe_n.features_to_consumer(hosts[1 % len(hosts)], qn_host, to_normals)
-        torch.cuda.synchronize()
+        nrm_host, exp_host, prob_host = est(hosts[1 % len(hosts)], qn_host)     # synchronises before it returns
         nt = time.perf_counter() - w0
+        n_n = int(nrm_host.shape[0])
         e2e["normals"] = {"value": n_n / nt, "unit": UNIT, "queries": n_n, "h2d_bytes_per_step": pipe_n.h2d_bytes,
-                          "d2h_bytes_per_step": n_n * 12, "chunk_queries": pipe_n.chunk, "finite": bool(torch.isfinite(normals_host).all()),
-                          "api": "host cloud in -> MuPSPipeline.features_to_consumer -> moe_engine.TensorCoreExperts.predict (tcgen05 conv3d, "
-                                 "bf16 x bf16 -> fp32) -> normals to pinned host memory; random-init 7-expert network, one GPU",
+                          "d2h_bytes_per_step": n_n * (12 + 8 + 4 * int(prob_host.shape[1])), "chunk_queries": pipe_n.chunk,
+                          "finite": bool(np.isfinite(nrm_host).all()),
+                          "api": "inference.CloudNormalEstimator: host cloud in -> MuPSPipeline.features_to_consumer -> "
+                                 "moe_engine.TensorCoreExperts.predict (tcgen05 conv3d, bf16 x bf16 -> fp32) -> normals, experts, "
+                                 "probabilities to pinned host memory; random-init 7-expert network, one GPU",
                           "cudnn_strict_fp32_queries_per_s": 774, "cudnn_source": "profiles/r02_moe.jsonl"}
-        del tc, pipe_n
+        del tc, pipe_n, est
 
     cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                     "sample": "measured at N=1 only (see the N=1 line / --impl reference)"}

@@ -909,6 +909,30 @@ def test_inference_driver(tmp_path):
         assert mb.evaluate.evaluate_shape(normals, ref_n.numpy())["pgp5"] > 0.99
 
 
+def test_cloud_normal_estimator_matches_the_dataset_driver(tmp_path):
+    """inference.CloudNormalEstimator (no patch tensor, MuPS consumed on the device by the tensor-core engine) returns what
+    inference.estimate_normals (reference-shaped dataset loop, patches materialised) returns for the same cloud."""
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator
+    from nesti_net_b200.inference import CloudNormalEstimator, estimate_normals
+    from nesti_net_b200.moe_engine import TensorCoreExperts
+    radius, P = [0.01, 0.03, 0.05, 0.07], 512
+    pts = orc.synthetic_cloud(3000, cloud_id=21)
+    np.savetxt(tmp_path / "shape.xyz", pts, fmt="%.9g")
+    (tmp_path / "list.txt").write_text("shape\n")
+    pts = np.loadtxt(tmp_path / "shape.xyz").astype(np.float32)      # what the dataset will read back
+    gmm = mb.get_3d_grid_gmm([8, 8, 8], 0.0156)
+    torch.manual_seed(7)
+    tc = TensorCoreExperts(ExpertsNormalEstimator(n_rads=4, n_gaussians=512, n_experts=7).eval().cuda())
+    ref = estimate_normals(str(tmp_path), "list.txt", str(tmp_path / "out"), tc, gmm, radius, P, batch_size=700, write=False)["shape"]
+    got = CloudNormalEstimator(tc, gmm, radius, P, seed=SEED, chunk=1024)(pts)
+    assert got[0].shape == (3000, 3) and got[1].shape == (3000,) and got[2].shape == (3000, 7)
+    assert np.array_equal(got[1], ref[1])
+    assert np.allclose(got[0], ref[0], atol=1e-6) and np.allclose(got[2], ref[2], atol=1e-6)
+    sub = np.arange(5, 3000, 7)
+    part = CloudNormalEstimator(tc, gmm, radius, P, seed=SEED)(pts, sub)
+    assert np.array_equal(part[1], ref[1][sub]) and np.allclose(part[0], ref[0][sub], atol=1e-6)
+
+
 def _conv_reference(x, cin_off, cin, w, scale, shift, relu, k):
     """fp32 reference of mups_conv3d_bn_relu on the bf16-rounded operands: TF 'SAME' cross-correlation, scale / shift, ReLU."""
     import torch.nn.functional as F
