@@ -83,8 +83,9 @@ int64_t mups_launch_count(void);
  * centres) and "hier_margin" (-1 = automatic; extra expected candidates above P kept by the hierarchical kernel's key
  * threshold; tests set 0 to exercise the hand-over to the flat kernel): results never depend on any of them.
  * "pool_variant" (0 = automatic: shared-memory tile + separable box sum for the 8^3 average pools; 1 = the per-voxel
- * kernel everywhere) and "conv_variant" (0 = automatic: two CTAs per SM for the short-K 1^3 layers; 1 = always one CTA per
- * SM with the deepest pipeline): benchmarking only. */
+ * kernel everywhere) and "conv_variant" (0 = automatic; 1 = one CTA per SM with the deepest pipeline also for the short-K 1^3
+ * layers; 2 = the per-tap kernel also for the 8^3 layers; 3 = z-halo kernel without the operand swap; 4 = half-sample CTAs
+ * at every batch size): benchmarking only. */
 int mups_set_option(const char* name, int64_t value);
 
 /* ---- spatial index (K1 bbox + K2 grid build) --------------------------------------------- */
