@@ -724,7 +724,7 @@ def run_clouds(args, cfg):
     # ---- the reference's user-visible path (test_n_est_w_experts.py:129-197): host cloud in -> MuPS -> Mixture-of-Experts ->
     # normals out, with the consumer on the tensor cores (moe_engine.TensorCoreExperts: hand-written tcgen05 conv3d, random-init
     # network) fed chunk by chunk through MuPSPipeline.features_to_consumer, so MuPS never leaves the device
-    if "e2e" not in skip and "normals" not in skip and RES == 8 and rank == 0:
+    if "e2e" not in skip and "normals" not in skip and RES == 8:        # every rank: its own cloud, its own consumer (data parallel)
         from nesti_net_b200.experts_net import ExpertsNormalEstimator
         from nesti_net_b200.moe_engine import TensorCoreExperts
         torch.manual_seed(1234)
@@ -736,17 +736,19 @@ def run_clouds(args, cfg):
         qn_host = (torch.arange(nq_n, dtype=torch.int64) * (N_POINTS // nq_n)).pin_memory()
         est(hosts[0], qn_host[:2048])                                   # warm-up (allocations, tensor maps)
         torch.cuda.synchronize()
+        barrier()
         pipe_n.h2d_bytes = 0
         w0 = time.perf_counter()
-        nrm_host, exp_host, prob_host = est(hosts[1 % len(hosts)], qn_host)     # synchronises before it returns
-        nt = time.perf_counter() - w0
+        nrm_host, exp_host, prob_host = est(hosts[(1 + rank) % len(hosts)], qn_host)     # synchronises before it returns
+        nt = max_over_ranks(time.perf_counter() - w0, dev, world)
+        barrier()
         n_n = int(nrm_host.shape[0])
-        e2e["normals"] = {"value": n_n / nt, "unit": UNIT, "queries": n_n, "h2d_bytes_per_step": pipe_n.h2d_bytes,
+        e2e["normals"] = {"value": n_n * n_gpus / nt, "unit": UNIT, "queries": n_n * n_gpus, "h2d_bytes_per_step": pipe_n.h2d_bytes,
                           "d2h_bytes_per_step": n_n * (12 + 8 + 4 * int(prob_host.shape[1])), "chunk_queries": pipe_n.chunk,
                           "finite": bool(np.isfinite(nrm_host).all()),
                           "api": "inference.CloudNormalEstimator: host cloud in -> MuPSPipeline.features_to_consumer -> "
                                  "moe_engine.TensorCoreExperts.predict (tcgen05 conv3d, bf16 x bf16 -> fp32) -> normals, experts, "
-                                 "probabilities to pinned host memory; random-init 7-expert network, one GPU",
+                                 "probabilities to pinned host memory; random-init 7-expert network; every rank its own cloud and consumer",
                           "cudnn_strict_fp32_queries_per_s": 774, "cudnn_source": "profiles/r02_moe.jsonl"}
         del tc, pipe_n, est
 
