@@ -107,7 +107,7 @@ void mups_index_destroy(mups_index* index);
  *   nbr_total[b][s] = |{ j : sum_k (double(p_jk) - double(p_ck))^2 <= r*r }|  (cKDTree predicate)
  *   n_eff[b][s]     = min(P, nbr_total)
  *   the shared seeded selection when nbr_total > P, else all neighbours, in ascending index order:
- *   (a, b) = Philox4x32-10(counter=(centre, s, 0, 0), key=seed)[0..1], key(j) = fmix32((j ^ a) * (b | 1));
+ *   (a, b) = Philox4x32-10(counter=(centre, s, 0, 0), key=seed)[0..1], key(j) = (fmix32(j) ^ a) * (b | 1) mod 2^32;
  *   the P smallest (key, j) pairs are kept (oracle/mups_oracle.py::select_subset)
  *   nbr_idx[b][s][t]      = selected point index, -1 beyond n_eff           (may be NULL)
  *   patches[b][s*P+t][k]  = (p_jk - p_ck) / float(r_s) in IEEE fp32, 0 beyond n_eff (may be NULL)

@@ -140,7 +140,7 @@ void mups_index_destroy(mups_index* ix) {
     if (ix->cell_start) cudaFreeAsync(ix->cell_start, ix->build_stream);
     if (ix->pos_of) cudaFreeAsync(ix->pos_of, ix->build_stream);
     if (ix->codes) cudaFreeAsync(ix->codes, ix->build_stream);
-    if (ix->idx_sorted) cudaFreeAsync(ix->idx_sorted, ix->build_stream);
+    if (ix->hash_sorted) cudaFreeAsync(ix->hash_sorted, ix->build_stream);
     if (prev >= 0) cudaSetDevice(prev);
     delete ix;
 }
@@ -189,7 +189,7 @@ int mups_index_create(mups_index** out, const float* xyz_dev, int64_t n, double 
     if ((rc = alloc((void**)&ix->cell_start, sizeof(uint32_t) * (size_t)(n_scan + n_tiles + 8)))) return fail(rc);
     if ((rc = alloc((void**)&ix->pos_of, sizeof(int32_t) * (size_t)n))) return fail(rc);
     if ((rc = alloc((void**)&ix->codes, sizeof(uint32_t) * (size_t)(n < 8 ? 8 : n)))) return fail(rc);
-    if ((rc = alloc((void**)&ix->idx_sorted, sizeof(int32_t) * (size_t)n))) return fail(rc);
+    if ((rc = alloc((void**)&ix->hash_sorted, sizeof(uint32_t) * (size_t)n))) return fail(rc);
     ix->build_stream = st;
     if ((rc = launch_index_build(ix, xyz_dev, st))) return fail(rc);
     if (cudaEventCreateWithFlags(&ix->built, cudaEventDisableTiming) != cudaSuccess ||

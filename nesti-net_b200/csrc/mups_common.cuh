@@ -78,8 +78,8 @@ struct mups_index {
     uint32_t* cell_start = nullptr;      // device [ncode + 1]: exclusive prefix of cell populations
     int32_t* pos_of = nullptr;           // device [n]: position in `sorted` of original point i
     uint32_t* codes = nullptr;           // device [n]: Morton cell code per original point (build scratch, kept)
-    int32_t* idx_sorted = nullptr;       // device [n]: original index of sorted[i] alone (4 B/point: the hierarchical
-                                         // query reads only this for cells wholly inside a ball)
+    uint32_t* hash_sorted = nullptr;     // device [n]: point_hash(original index of sorted[i]) (4 B/point: all the hierarchical
+                                         // query reads of a point in a cell wholly inside a ball)
     cudaStream_t build_stream = nullptr;
     cudaEvent_t built = nullptr;
     // host copy of the bbox, fetched lazily by mups_index_bbox
@@ -155,6 +155,13 @@ __device__ __forceinline__ int cell_coord(float p, float origin, float inv_cell,
 }
 
 // Philox4x32-10 (Random123 constants); counter (c0..c3), key (k0,k1)
+// murmur3's 32-bit finaliser (a bijection): the patch-independent hash of a point index in the shared seeded selection
+// (oracle/mups_oracle.py::selection_keys); stored per point by the index build (mups_index::hash_sorted)
+__device__ __forceinline__ uint32_t point_hash(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1) {
 #pragma unroll

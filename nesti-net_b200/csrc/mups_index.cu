@@ -168,13 +168,13 @@ __global__ void __launch_bounds__(256) scatter_kernel(const float* __restrict__ 
                                                       const uint32_t* __restrict__ codes,
                                                       const uint32_t* __restrict__ cell_start,
                                                       int32_t* __restrict__ pos_of /* in: rank, out: position */,
-                                                      float4* __restrict__ sorted, int32_t* __restrict__ idx_sorted) {
+                                                      float4* __restrict__ sorted, uint32_t* __restrict__ hash_sorted) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t pos = (int32_t)(cell_start[codes[i]] + (uint32_t)pos_of[i]);
         pos_of[i] = pos;
         sorted[pos] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2),
                                   __int_as_float((int)i));
-        idx_sorted[pos] = (int32_t)i;
+        hash_sorted[pos] = point_hash((uint32_t)i);      // patch-independent half of the selection key
     }
 }
 
@@ -211,7 +211,7 @@ int launch_index_build(mups_index* ix, const float* xyz, cudaStream_t st) {
     uint32_t* tile_sums = ix->cell_start + n_scan;            // allocated with n_tiles extra entries
     if (int rc = launch_exclusive_scan(ix->cell_start, n_scan, tile_sums, st)) return rc;
 
-    scatter_kernel<<<grid, 256, 0, st>>>(xyz, n, ix->codes, ix->cell_start, ix->pos_of, ix->sorted, ix->idx_sorted);
+    scatter_kernel<<<grid, 256, 0, st>>>(xyz, n, ix->codes, ix->cell_start, ix->pos_of, ix->sorted, ix->hash_sorted);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;
 }

@@ -59,7 +59,7 @@ struct QueryArgs {
     float r2_hi_max;
     uint32_t k0, k1;                // philox key = seed
     // hierarchical kernel
-    const int32_t* idx_sorted;
+    const uint32_t* hash_sorted;
     int bits;                       // Morton bits per axis of the leaf level
     uint32_t ccap;                  // candidate positions kept per radius
     uint32_t want;                  // P + 6 sqrt(P) + 8: expected candidates under the key threshold
@@ -85,6 +85,7 @@ struct ScanTables {
     uint32_t start[kRangeCap];
     uint32_t prefix[kRangeCap + 1];
     uint32_t first_total;           // candidates of the first batch of the last scan (all 27 cells when R = 1)
+    uint32_t n_ranges, total;       // non-empty cells of the batch (start / prefix hold only those), candidates of the batch
 };
 
 // cKDTree leaf predicate: s = 0; s += d*d for x, y, z in float64 without FMA contraction; s <= r*r
@@ -127,23 +128,26 @@ __device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx&
                 }
             }
             uint32_t inc = cnt[0] + cnt[1];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
+            uint32_t slots = (cnt[0] ? 1u : 0u) + (cnt[1] ? 1u : 0u);       // only non-empty cells get a table entry: the
+#pragma unroll                                                              // scan's walk over the table is a tenth of the
+            for (int o = 1; o < 32; o <<= 1) {                              // kernel's instructions on surface clouds, where
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);     // two thirds of the 27 cells are empty
+                const uint32_t u = __shfl_up_sync(0xffffffffu, slots, o);
+                if (lane >= o) { inc += t; slots += u; }
             }
             const uint32_t exc = inc - cnt[0] - cnt[1];
-            st.start[2 * lane] = beg[0];
-            st.start[2 * lane + 1] = beg[1];
-            st.prefix[2 * lane] = exc;
-            st.prefix[2 * lane + 1] = exc + cnt[0];
+            uint32_t e = slots - (cnt[0] ? 1u : 0u) - (cnt[1] ? 1u : 0u);
+            if (cnt[0]) { st.start[e] = beg[0]; st.prefix[e] = exc; ++e; }
+            if (cnt[1]) { st.start[e] = beg[1]; st.prefix[e] = exc + cnt[0]; }
             if (lane == 31) {
-                st.prefix[kRangeCap] = inc;
+                st.prefix[slots] = inc;          // end sentinel of the compacted table
+                st.n_ranges = slots;
+                st.total = inc;
                 if (cbase == 0) st.first_total = inc;
             }
         }
         __syncthreads();
-        const uint32_t total = st.prefix[kRangeCap];
+        const uint32_t total = st.total;
         int k = 0;
         for (uint32_t fi = tid; fi < total; fi += kQT) {
             while (fi >= st.prefix[k + 1]) ++k;
@@ -169,21 +173,20 @@ __device__ __forceinline__ void for_each_hit(const QueryArgs& a, const QueryCtx&
     }
 }
 
-// key of neighbour `idx` for radius s: fmix32((idx ^ a_s) * b_s), a bijection of idx keyed by the salt
-// (a_s, b_s | 1) = Philox4x32-10(counter = (centre, s, 0, 0), key = seed) computed once per CTA and radius
+// key of neighbour `idx` for radius s: (fmix32(idx) ^ a_s) * b_s, a bijection of idx keyed by the salt
+// (a_s, b_s | 1) = Philox4x32-10(counter = (centre, s, 0, 0), key = seed) computed once per CTA and radius; fmix32(idx) is
+// patch-independent: once per neighbour here, read from the index (hash_sorted) in the hierarchical kernel
 struct Salts {
     uint32_t a[MUPS_MAX_SCALES], b[MUPS_MAX_SCALES];
 };
-__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
-    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
-    return h;
-}
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) { return point_hash(h); }
 template <int NS>
 __device__ __forceinline__ void selection_keys(const Salts& salt, uint32_t idx, uint32_t need_mask,
                                                uint32_t key[MUPS_MAX_SCALES]) {
+    const uint32_t h = fmix32(idx);
 #pragma unroll
     for (int s = 0; s < NS; ++s)
-        if (need_mask & (1u << s)) key[s] = fmix32((idx ^ salt.a[s]) * salt.b[s]);
+        if (need_mask & (1u << s)) key[s] = (h ^ salt.a[s]) * salt.b[s];
 }
 
 // One warp finds, in hist[0..nbins), the bin T holding the `need`-th smallest element.
@@ -466,7 +469,13 @@ __device__ __forceinline__ void ball_query_flat_one(const QueryArgs& a, const in
         for_each_hit<NS>(a, c, st, [&](uint32_t pos, uint32_t idx, uint32_t in) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) cnt[s] += (in >> s) & 1u;
-            const uint32_t slot = atomicAdd(&s_nhits, 1u);
+            // one shared-memory atomic per warp instead of one per hit (half of the candidates are hits; the counter is a
+            // single address)
+            const unsigned peers = __activemask();
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&s_nhits, (uint32_t)__popc(peers));
+            const uint32_t slot = __shfl_sync(peers, base, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
             if (slot < (uint32_t)kHitCap) { hit_pos[slot] = pos; hit_mask[slot] = (unsigned char)in; }
             if (st.first_total > a.fuse) {
                 // dense neighbourhood: the hit list will overflow and every later pass re-scans the cells, so
@@ -875,13 +884,13 @@ __global__ void __launch_bounds__(kHT, 3) ball_query_hier_kernel(const QueryArgs
             const uint32_t test = count ? straddle : (straddle & collect);
             if (test == 0u) {
                 if (!(inside & collect)) continue;
-                // wholly inside: only the point indices are read (4 bytes per neighbour)
+                // wholly inside: only the points' patch-independent hashes are read (4 bytes per neighbour)
                 for (uint32_t i0 = 0; i0 < n; i0 += 128) {
                     uint32_t idx[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const uint32_t i = i0 + u * 32 + lane;
-                        idx[u] = i < n ? (uint32_t)__ldg(a.idx_sorted + start + i) : 0xFFFFFFFFu;
+                        idx[u] = i < n ? __ldg(a.hash_sorted + start + i) : 0xFFFFFFFFu;
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -890,7 +899,7 @@ __global__ void __launch_bounds__(kHT, 3) ball_query_hier_kernel(const QueryArgs
 #pragma unroll
                         for (int s = 0; s < NS; ++s) {
                             if (!((inside & collect) & (1u << s))) continue;
-                            const uint32_t key = fmix32((idx[u] ^ salt.a[s]) * salt.b[s]);
+                            const uint32_t key = (idx[u] ^ salt.a[s]) * salt.b[s];
                             if (key <= Ts[s]) {
                                 const uint32_t slot = atomicAdd(s_ncand + s, 1u);
                                 if (slot < ccap) cand[s * ccap + slot] = start + i;
@@ -921,11 +930,11 @@ __global__ void __launch_bounds__(kHT, 3) ball_query_hier_kernel(const QueryArgs
                     }
                     in &= collect;
                     if (!in) continue;
-                    const uint32_t idx = (uint32_t)__float_as_int(p.w);
+                    const uint32_t hsh = fmix32((uint32_t)__float_as_int(p.w));
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         if (!(in & (1u << s))) continue;
-                        const uint32_t key = fmix32((idx ^ salt.a[s]) * salt.b[s]);
+                        const uint32_t key = (hsh ^ salt.a[s]) * salt.b[s];
                         if (key <= Ts[s]) {
                             const uint32_t slot = atomicAdd(s_ncand + s, 1u);
                             if (slot < ccap) cand[s * ccap + slot] = start + i;
@@ -981,8 +990,7 @@ __global__ void __launch_bounds__(kHT, 3) ball_query_hier_kernel(const QueryArgs
             if (!(over & (1u << s))) continue;
             const uint32_t nc = s_ncand[s], sc = s_scale[s];
             for (uint32_t i = tid; i < nc; i += kHT) {
-                const uint32_t idx = (uint32_t)__ldg(a.idx_sorted + cand[s * ccap + i]);
-                const uint32_t key = fmix32((idx ^ salt.a[s]) * salt.b[s]);
+                const uint32_t key = (__ldg(a.hash_sorted + cand[s * ccap + i]) ^ salt.a[s]) * salt.b[s];
                 atomicAdd(hist + s * kBins + min((uint32_t)(kBins - 1), __umulhi(key, sc)), 1u);
             }
         }
@@ -1007,10 +1015,10 @@ __global__ void __launch_bounds__(kHT, 3) ball_query_hier_kernel(const QueryArgs
         const uint32_t sc = s_scale[s], tb = s_tbin[s];
         for (uint32_t i = tid; i < nc; i += kHT) {
             const uint32_t pos = cand[s * ccap + i];
-            const uint32_t idx = (uint32_t)__ldg(a.idx_sorted + pos);
+            const uint32_t idx = (uint32_t)__float_as_int(__ldg(&a.sorted[pos].w));
             bool take = true;
             if (thin) {
-                const uint32_t key = fmix32((idx ^ salt.a[s]) * salt.b[s]);
+                const uint32_t key = (__ldg(a.hash_sorted + pos) ^ salt.a[s]) * salt.b[s];
                 const uint32_t bin = min((uint32_t)(kBins - 1), __umulhi(key, sc));
                 take = bin < tb;
                 if (bin == tb) {
@@ -1091,7 +1099,7 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
     a.r2_hi_max = hi_max;
     a.k0 = (uint32_t)(seed & 0xFFFFFFFFull); a.k1 = (uint32_t)(seed >> 32);
     a.nbr_idx = nbr_idx; a.nbr_total = nbr_total; a.patches = patches; a.n_eff = n_eff; a.nbr_pos = nbr_pos;
-    a.idx_sorted = ix->idx_sorted; a.bits = ix->bits;
+    a.hash_sorted = ix->hash_sorted; a.bits = ix->bits;
     const int margin = g_hier_margin.load();
     a.want = (uint32_t)P + (margin >= 0 ? (uint32_t)margin : (uint32_t)std::ceil(6.0 * std::sqrt((double)P)) + 8u);
     a.ccap = (uint32_t)(P <= 512 ? (3 * P > 1024 ? 3 * P : 1024) : (5 * P) / 2);
@@ -1111,7 +1119,7 @@ int launch_ball_query(const mups_index* ix, const int64_t* q, int64_t B, const d
     const size_t smem_h = (size_t)kSegCap * 12 + hq + (size_t)S * ppad * 8 + (size_t)S * kBoundaryCap * 12 + region_h;
     const int mode = g_query_kernel.load();
     const bool hier = mode == 2 || (mode == 0 && ix->bits >= 6);
-    const bool use_hier = hier && smem_h <= 112 * 1024 && ix->idx_sorted != nullptr;
+    const bool use_hier = hier && smem_h <= 112 * 1024 && ix->hash_sorted != nullptr;
 
     cudaMemPool_t pool = nullptr;
     int32_t* scratch = nullptr;      // [order: B][worklist: B][work_count: 1][buckets + scan tiles]

@@ -319,7 +319,7 @@ int oracle_mups_f64(const float* points, const int32_t* n_eff, const float* w, c
 
 /* The shared seeded selection key, see oracle/mups_oracle.py::selection_keys:
  * (a, b) = first two words of Philox4x32-10(counter = (center, scale, 0, 0), key = seed);
- * key(j) = fmix32((j ^ a) * (b | 1)).  out[i] = key of neighbour nbr[i]. */
+ * key(j) = (fmix32(j) ^ a) * (b | 1) mod 2^32.  out[i] = key of neighbour nbr[i]. */
 static uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
@@ -337,7 +337,7 @@ void oracle_selection_keys(uint64_t seed, uint32_t center, uint32_t scale, const
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     const uint32_t a = c0, b = c1 | 1u;
-    for (int64_t i = 0; i < n; ++i) out[i] = fmix32(((uint32_t)nbr[i] ^ a) * b);
+    for (int64_t i = 0; i < n; ++i) out[i] = (fmix32((uint32_t)nbr[i]) ^ a) * b;
 }
 
 /* ---- half 1 after the kd-tree query: shared seeded selection + gather + centre + normalise (pcpnet_dataset.py:310-343)
@@ -401,7 +401,7 @@ int oracle_half1_gather(const float* pts, const int64_t* query_idx, int64_t B, f
                 }
             }
             if (n > P) {
-                /* Philox4x32-10(counter = (centre, scale, 0, 0), key = seed) -> salt (a, b | 1); key(j) = fmix32((j ^ a) * b) */
+                /* Philox4x32-10(counter = (centre, scale, 0, 0), key = seed) -> salt (a, b | 1); key(j) = (fmix32(j) ^ a) * b */
                 uint32_t c0 = (uint32_t)c, c1 = (uint32_t)scale, c2 = 0, c3 = 0;
                 uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
                 for (int r = 0; r < 10; ++r) {
@@ -413,7 +413,7 @@ int oracle_half1_gather(const float* pts, const int64_t* query_idx, int64_t B, f
                 }
                 const uint32_t sa = c0, sb = c1 | 1u;
                 for (int64_t i = 0; i < n; ++i)
-                    keyed[i] = ((uint64_t)fmix32(((uint32_t)nb[i] ^ sa) * sb) << 32) | (uint32_t)nb[i];
+                    keyed[i] = ((uint64_t)((fmix32((uint32_t)nb[i]) ^ sa) * sb) << 32) | (uint32_t)nb[i];
                 select_smallest(keyed, n, P);                                /* the P smallest (key, index) pairs */
                 for (int64_t i = 0; i < P; ++i) sel[i] = (int64_t)(keyed[i] & 0xFFFFFFFFull);
                 qsort(sel, (size_t)P, sizeof(int64_t), cmp_i64);

@@ -76,6 +76,32 @@ def test_selection_rule_properties():
     assert np.array_equal(orc.select_subset(small[::-1], 64, 1, 2, 0), small)          # no subsample needed
 
 
+def test_selection_rule_is_a_uniform_sample():
+    """The shared seeded selection draws uniform P-subsets: over 1 500 centres and one fixed neighbour set (random and
+    contiguous indices) the per-point selection counts and the pair co-selection counts sit at their hypergeometric
+    expectations (chi-square within 5 standard deviations of its degrees of freedom), and the subsets of two scales of the
+    same centre overlap like independent draws."""
+    n, P, T = 1500, 256, 1500
+    for nbr in (np.sort(np.random.RandomState(1).choice(100000, n, replace=False)), np.arange(70000, 70000 + n)):
+        cnt, pair, overlap = np.zeros(n), np.zeros((40, 40)), []
+        for c in range(T):
+            sel = np.zeros(n, bool)
+            sel[np.argsort(orc.selection_keys(3627473, c, 2, nbr).astype(np.int64), kind="stable")[:P]] = True
+            sel2 = np.zeros(n, bool)
+            sel2[np.argsort(orc.selection_keys(3627473, c, 3, nbr).astype(np.int64), kind="stable")[:P]] = True
+            cnt += sel
+            pair += np.outer(sel[:40], sel[:40])
+            overlap.append(int((sel & sel2).sum()))
+        p, pp = P / n, P * (P - 1) / (n * (n - 1))
+        chi = ((cnt - T * p) ** 2 / (T * p * (1 - p))).sum()
+        assert abs(chi - n) < 5 * np.sqrt(2 * n), chi
+        off = pair[np.triu_indices(40, 1)]
+        chi2 = ((off - T * pp) ** 2 / (T * pp * (1 - pp))).sum()
+        assert abs(chi2 - len(off)) < 5 * np.sqrt(2 * len(off)), chi2
+        sd = np.sqrt(P * p * (1 - p) * (n - P) / (n - 1))                        # hypergeometric
+        assert abs(np.mean(overlap) - P * p) < 5 * sd / np.sqrt(T) and 0.8 * sd < np.std(overlap) < 1.2 * sd
+
+
 def test_philox_known_answers_and_c_port():
     # Random123 known-answer vectors for philox4x32-10
     assert [int(x) for x in orc.philox4x32_10(0, 0, 0, 0, 0, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
