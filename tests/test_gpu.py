@@ -1111,6 +1111,40 @@ def test_tensor_core_consumer_against_reference_text(golden_dir):
     assert rms < 1.0 and dprob < 0.02 and torch.equal(prob.argmax(0), ref_prob.argmax(0))
 
 
+def test_tensor_core_consumer_three_scales():
+    """BASELINE configs[0] has three scales: seven experts = two per scale + one three-scale expert whose first inception
+    module is 128 / 3 = 42 filters wide (Python-2 division, models/experts_n_est.py:254) -- channel counts that are not
+    multiples of 16 go through the padded layouts of the engine (42 -> 48, 21 -> 32)."""
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg
+    from nesti_net_b200.moe_engine import TensorCoreExperts
+    pts = orc.synthetic_cloud(20000, cloud_id=4, noise=0.001)
+    radius, P = [0.01, 0.03, 0.07], 512
+    w, mu, sg = grid_gmm(8, 0.0156)
+    q = np.random.RandomState(3).choice(20000, 96, replace=False)
+    index = mb.PointIndex(pts, cell_frac=max(radius))
+    mups = mb.mups_features(index, mb.gmm_handle(w, mu, sg), q, index.absolute_radii(radius), P, seed=SEED)
+    torch.manual_seed(99)
+    net = ExpertsNormalEstimator(n_rads=3, n_gaussians=512, n_experts=7).eval()
+    assert net.expert_dict[6] == [0, 1, 2] and net.expert_conv[6].mods[0].one.conv.out_channels == 42
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, (torch.nn.BatchNorm3d, torch.nn.BatchNorm1d)):
+                m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.6, 1.5); m.weight.uniform_(0.7, 1.3); m.bias.normal_(0, 0.05)
+    net = net.cuda()
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            prob_ref, n_ref = net(mups)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    prob, n_est = TensorCoreExperts(net).forward(mups)
+    torch.cuda.synchronize()
+    same = prob.argmax(0) == prob_ref.argmax(0)
+    rms = angular_rms_deg(n_est.reshape(-1, 3), n_ref.reshape(-1, 3))
+    assert torch.isfinite(n_est).all() and rms < 1.0 and int(same.sum()) >= int(0.9 * len(q)) and float((prob - prob_ref).abs().max()) < 0.05
+
+
 def test_downstream_moe_normals():
     """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
     models/experts_n_est.py, fp32) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4 angular
