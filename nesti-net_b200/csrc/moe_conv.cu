@@ -690,6 +690,28 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
     // two voxel tiles per CTA share one weight tile when both accumulators fit the 256 TMEM columns and the layer is deep
     // enough for operand delivery to matter (g_conv_m_sub: benchmarking override)
     a.m_sub = (n_tile <= 128 && m_tiles >= 2 * kNumSMs && k > 1) ? 2 : 1;
+    if (k > 1 && D < 8 && ((m_tiles + a.m_sub - 1) / a.m_sub) * (cout / n_tile) < kNumSMs / 4 && g_conv_variant.load() != 5) {
+        // nearly empty grids (a 2^3 layer of a 256-query batch is 16 tiles -- 16 CTAs on 148 SMs; measured: +2.5 % on the whole
+        // forward at batch 256, while splitting grids of 64 or more CTAs gains nothing -- their K loop is latency-bound).  Pick the
+        // (channel tile, voxel tiles per CTA) with the lowest estimated time = waves x per-CTA cost (relative time per
+        // 64-channel stage: N = 256 1.0, N = 128 0.62, N = 64 0.5 -- the narrow tiles pay more operand reads and more L2
+        // traffic per FLOP, measured: splitting a grid that already fills the machine loses), and only when it wins by 15 %
+        const int cands[3] = {n_tile, 128, 64};
+        const double rel[3] = {n_tile >= 256 ? 1.0 : n_tile >= 128 ? 0.62 : 0.5 * n_tile / 64.0, 0.62, 0.5};
+        int best_n = n_tile, best_ms = a.m_sub;
+        const long long ctas0 = ((m_tiles + a.m_sub - 1) / a.m_sub) * (cout / n_tile);
+        double best = 0.85 * (double)((ctas0 + kNumSMs - 1) / kNumSMs) * a.m_sub * rel[0] * (a.m_sub == 2 ? 0.95 : 1.0);
+        for (int c = 1; c < 3; ++c) {
+            const int n = cands[c];
+            if (n >= n_tile || cout % n) continue;
+            for (int ms = 1; ms <= 2; ++ms) {
+                const long long ctas = ((m_tiles + ms - 1) / ms) * (cout / n);
+                const double t = (double)((ctas + kNumSMs - 1) / kNumSMs) * ms * rel[c] * (ms == 2 ? 0.95 : 1.0);
+                if (t < best - 1e-9) { best = t; best_n = n; best_ms = ms; }
+            }
+        }
+        n_tile = best_n; a.n_tile = n_tile; a.m_sub = best_ms;
+    }
     if (const char* e = getenv("MUPS_CONV_M_SUB")) a.m_sub = (atoi(e) == 2 && n_tile <= 128) ? 2 : 1;
     const int stage_bytes = a.m_sub * kABytes + n_tile * kTileK * 2;
     int stages = (200 * 1024) / stage_bytes;
