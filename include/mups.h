@@ -184,6 +184,21 @@ int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off
 int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin,
                         const void* w_bf16_dev, int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev,
                         int relu, void* y_bf16_dev, int cout_total, int cout_off, float* y_f32_dev, mups_stream stream);
+/* The two 1^3 convolutions of an inception module that read the module's input -- `one` (utils/tf_util.py conv3d, scope
+ * '_conv1') and the convolution after the average pool ('_conv4', models/experts_n_est.py:291-310) -- from ONE read of it.
+ * A 1^3 convolution without bias commutes with the average pool (both are linear, one over channels, one over voxels), so
+ * conv4(avgpool(x)) = avgpool(conv4_nobias(x)) + bias: the pool then runs on n_filters instead of C_in channels.
+ * w_bf16_dev: [1][cout][cin_w], rows [0, split) = conv1, rows [split, cout) = conv4; scale / shift per output channel (identity
+ * for the rows whose batch norm is applied after the pool); ReLU on output channels below relu_upto.  Channels [0, split) go to
+ * channels [y1_off, ...) of y1_bf16_dev [.., y1_total], channels [split, cout) to [y2_off, ...) of y2_bf16_dev [.., y2_total]. */
+int mups_conv1_split_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
+                             int cin_w, int cout, const float* scale_dev, const float* shift_dev, int relu_upto, void* y1_bf16_dev,
+                             int y1_total, int y1_off, int split, void* y2_bf16_dev, int y2_total, int y2_off, mups_stream stream);
+/* tf_util.avg_pool3d (window k >= 2, stride 1, 'SAME', mean over the valid cells) of channels [c_off, c_off + c) of x_bf16_dev
+ * followed by y = act(scale[ch] * pooled + shift[ch]) into channels [y_off, y_off + c) of y_bf16_dev [B, D, D, D, y_total]: the
+ * second half of the pool branch above. */
+int mups_avgpool3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, const float* scale_dev,
+                           const float* shift_dev, int relu, void* y_bf16_dev, int y_total, int y_off, mups_stream stream);
 
 #ifdef __cplusplus
 }

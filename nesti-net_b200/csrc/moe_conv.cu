@@ -50,7 +50,13 @@ struct ConvArgs {
     long long y_stride;              // channels per voxel of the output tensor
     int cout_off;                    // first output channel written
     float* y_f32;                    // optional fp32 output [rows, Cout] (last layers), or nullptr
-};
+    // split destination (1^3 layers that compute two branches of an inception module from one read of the input): output
+    // channels [split, Cout) go to channels [y2_off, ...) of y2 instead; ReLU only on channels below relu_upto
+    __nv_bfloat16* y2;
+    long long y2_stride;
+    int y2_off, split, relu_upto;
+    int n_tiles, m_ctas, n_fast;     // channel tiles per voxel tile, voxel-tile CTAs; the grid is 1-D: with n_fast the channel tile is
+};                                   // the FAST index, so that the CTAs that read the same activation tile run together (L2 hits)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -120,7 +126,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_ac
     const long long bsample = (long long)tb0[u] + bl;
     const bool live = bsample < a.B && tile0 + u < a.m_tiles;
     const long long voxel = ((bsample * a.D + (tz0[u] + zl)) * a.D + yy) * a.D + x;
-    __nv_bfloat16* yrow = a.y ? a.y + voxel * a.y_stride + a.cout_off + n0 : nullptr;
+    __nv_bfloat16* yrow = a.y ? (a.y2 && n0 >= a.split ? a.y2 + voxel * a.y2_stride + a.y2_off + (n0 - a.split)
+                                                        : a.y + voxel * a.y_stride + a.cout_off + n0) : nullptr;
     float* frow = a.y_f32 ? a.y_f32 + voxel * (long long)a.Cout + n0 : nullptr;
     for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
         uint32_t v[16];
@@ -131,7 +138,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_ac
             const int co = n0 + c0 + j;
             const float sc = co < a.Cout ? __ldg(a.scale + co) : 0.f, sh = co < a.Cout ? __ldg(a.shift + co) : 0.f;
             float t = fmaf(__uint_as_float(v[j]), sc, sh);
-            f[j] = a.relu ? fmaxf(t, 0.f) : t;
+            f[j] = (a.relu && co < a.relu_upto) ? fmaxf(t, 0.f) : t;
         }
         if (live) {
             if (yrow) {
@@ -192,9 +199,9 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     // this CTA's tiles: m_sub x 128 voxels x n_tile output channels
-    const int n0 = blockIdx.y * a.n_tile;
+    const int n0 = (int)(a.n_fast ? blockIdx.x % (unsigned)a.n_tiles : blockIdx.x / (unsigned)a.m_ctas) * a.n_tile;
     const int tiles_per_sample = (a.D * a.D * a.D + kTileM - 1) / kTileM;          // 4 for 8^3, else 1
-    const int tile0 = blockIdx.x * a.m_sub;
+    const int tile0 = (int)(a.n_fast ? blockIdx.x / (unsigned)a.n_tiles : blockIdx.x % (unsigned)a.m_ctas) * a.m_sub;
     int tb0[2], tz0[2];                          // first sample / first z-slice of each of this CTA's tiles (computed once: the
     for (int u = 0; u < 2; ++u) {                // producer issues a load every ~100 ns and cannot afford divisions)
         const int t = tile0 + u;
@@ -433,8 +440,10 @@ __global__ void __launch_bounds__(256) pack_mups_bf16_kernel(const float* __rest
 // tf.nn.avg_pool3d(ksize k, stride 1, 'SAME') on NDHWC bf16: mean over the VALID cells of each window (the padding does not
 // count, utils/tf_util.py:432-455), fp32 inside; and tf.nn.max_pool3d(2, stride 2) (:406-430).  One thread per (output voxel,
 // 8-channel chunk): 16-byte loads / stores, memory bound, the window re-reads hit L1 / L2.
+struct PoolEpi { const float* scale; const float* shift; int relu; int y_total, y_off; };   // scale == nullptr: plain pool, contiguous y
+
 __global__ void __launch_bounds__(256) pool3d_kernel(const __nv_bfloat16* __restrict__ x, long long B, int D, int ct, int c_off, int c,
-                                                     int k, int is_max, __nv_bfloat16* __restrict__ y) {
+                                                     int k, int is_max, __nv_bfloat16* __restrict__ y, const PoolEpi ep) {
     const int chunks = c >> 3;
     const int Do = is_max ? D / 2 : D;
     const long long n = B * Do * Do * Do * chunks;
@@ -474,9 +483,20 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const __nv_bfloat16* __rest
         const float inv = is_max ? 1.f : 1.f / (float)cnt;
         uint4 out;
         __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&out);
+        if (ep.scale) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
-        reinterpret_cast<uint4*>(y + v * (long long)c)[ch] = out;
+            for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(acc[j] * inv, __ldg(ep.scale + ch * 8 + j), __ldg(ep.shift + ch * 8 + j));
+                acc[j] = ep.relu ? fmaxf(t, 0.f) : t;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            reinterpret_cast<uint4*>(y + v * (long long)ep.y_total + ep.y_off)[ch] = out;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
+            reinterpret_cast<uint4*>(y + v * (long long)c)[ch] = out;
+        }
     }
 }
 
@@ -487,7 +507,7 @@ __global__ void __launch_bounds__(256) pool3d_kernel(const __nv_bfloat16* __rest
 // HBM traffic: every input and output byte once.
 template <int K>
 __global__ void __launch_bounds__(256) avgpool8_tile_kernel(const __nv_bfloat16* __restrict__ x, int ct, int c_off, int c,
-                                                            __nv_bfloat16* __restrict__ y) {
+                                                            __nv_bfloat16* __restrict__ y, const PoolEpi ep) {
     extern __shared__ __align__(16) float tile[];                  // [512 voxels][32 channels]
     constexpr int D = 8, PL = (K - 1) / 2;
     const int chunks = c >> 5;
@@ -535,7 +555,8 @@ __global__ void __launch_bounds__(256) avgpool8_tile_kernel(const __nv_bfloat16*
         }
         __syncthreads();
     }
-    __nv_bfloat16* dst = y + b * 512 * (long long)c + chunk * 32;
+    const int y_stride = ep.scale ? ep.y_total : c;
+    __nv_bfloat16* dst = y + b * 512 * (long long)y_stride + (ep.scale ? ep.y_off : 0) + chunk * 32;
     for (int i = tid; i < 512 * 4; i += 256) {
         const int v = i >> 2, part = i & 3;
         const int vx = v & 7, vy = (v >> 3) & 7, vz = v >> 6;
@@ -543,22 +564,29 @@ __global__ void __launch_bounds__(256) avgpool8_tile_kernel(const __nv_bfloat16*
         const float inv = 1.f / (float)(valid(vx) * valid(vy) * valid(vz));
         const float4* sp = reinterpret_cast<const float4*>(tile + v * 32 + part * 8);
         const float4 a0 = sp[0], a1 = sp[1];
+        float f[8] = {a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv, a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv};
+        if (ep.scale) {                       // folded bias + batch norm (+ ReLU) of the 1^3 convolution that ran BEFORE this pool
+            const int c0 = chunk * 32 + part * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(f[j], __ldg(ep.scale + c0 + j), __ldg(ep.shift + c0 + j));
+                f[j] = ep.relu ? fmaxf(t, 0.f) : t;
+            }
+        }
         uint4 out;
         __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&out);
-        o2[0] = __floats2bfloat162_rn(a0.x * inv, a0.y * inv);
-        o2[1] = __floats2bfloat162_rn(a0.z * inv, a0.w * inv);
-        o2[2] = __floats2bfloat162_rn(a1.x * inv, a1.y * inv);
-        o2[3] = __floats2bfloat162_rn(a1.z * inv, a1.w * inv);
-        reinterpret_cast<uint4*>(dst + v * (long long)c)[part] = out;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        reinterpret_cast<uint4*>(dst + v * (long long)y_stride)[part] = out;
     }
 }
 
 template <int K>
-static cudaError_t launch_avgpool8(const __nv_bfloat16* x, long long B, int ct, int c_off, int c, __nv_bfloat16* y, cudaStream_t st) {
+static cudaError_t launch_avgpool8(const __nv_bfloat16* x, long long B, int ct, int c_off, int c, __nv_bfloat16* y, const PoolEpi& ep, cudaStream_t st) {
     constexpr int smem = 512 * 32 * 4;
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(avgpool8_tile_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
-    avgpool8_tile_kernel<K><<<(unsigned)(B * (c >> 5)), 256, smem, st>>>(x, ct, c_off, c, y);
+    avgpool8_tile_kernel<K><<<(unsigned)(B * (c >> 5)), 256, smem, st>>>(x, ct, c_off, c, y, ep);
     return cudaGetLastError();
 }
 
@@ -622,20 +650,20 @@ int mups_moe_pack_input(const float* mups_dev, int64_t rows, int S, void* out_bf
     return MUPS_OK;
 }
 
-int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, int is_max, void* y_bf16_dev,
-                mups_stream stream) {
-    MUPS_REQUIRE(x_bf16_dev && y_bf16_dev, "mups_pool3d: NULL buffer");
-    MUPS_REQUIRE(B >= 1 && (D == 2 || D == 4 || D == 8), "mups_pool3d: B=%lld, volume edge %d", (long long)B, D);
-    MUPS_REQUIRE(c >= 8 && c % 8 == 0 && c_total % 8 == 0 && c_off % 8 == 0 && c_off + c <= c_total, "mups_pool3d: channels (%d of %d at %d) must be multiples of 8", c, c_total, c_off);
-    MUPS_REQUIRE(is_max ? k == 2 : (k >= 1 && k <= 5), "mups_pool3d: window %d", k);
+static int pool_launch(const char* who, const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, int is_max,
+                       void* y_bf16_dev, const PoolEpi& ep, mups_stream stream) {
+    MUPS_REQUIRE(x_bf16_dev && y_bf16_dev, "%s: NULL buffer", who);
+    MUPS_REQUIRE(B >= 1 && (D == 2 || D == 4 || D == 8), "%s: B=%lld, volume edge %d", who, (long long)B, D);
+    MUPS_REQUIRE(c >= 8 && c % 8 == 0 && c_total % 8 == 0 && c_off % 8 == 0 && c_off + c <= c_total, "%s: channels (%d of %d at %d) must be multiples of 8", who, c, c_total, c_off);
+    MUPS_REQUIRE(is_max ? k == 2 : (k >= 1 && k <= 5), "%s: window %d", who, k);
     if (!is_max && D == 8 && k >= 2 && c % 32 == 0 && (long long)B * (c >> 5) <= 0x7FFFFFFFll && g_pool_variant.load() != 1) {
         // shared-memory tile, separable box sum (every byte read once)
         const auto* xs = static_cast<const __nv_bfloat16*>(x_bf16_dev);
         auto* ys = static_cast<__nv_bfloat16*>(y_bf16_dev);
         const cudaStream_t st = static_cast<cudaStream_t>(stream);
-        cudaError_t e = k == 2 ? launch_avgpool8<2>(xs, B, c_total, c_off, c, ys, st) : k == 3 ? launch_avgpool8<3>(xs, B, c_total, c_off, c, ys, st)
-                      : k == 4 ? launch_avgpool8<4>(xs, B, c_total, c_off, c, ys, st) : launch_avgpool8<5>(xs, B, c_total, c_off, c, ys, st);
-        if (e != cudaSuccess) { set_error("mups_pool3d: %s", cudaGetErrorString(e)); return MUPS_ERR_CUDA; }
+        cudaError_t e = k == 2 ? launch_avgpool8<2>(xs, B, c_total, c_off, c, ys, ep, st) : k == 3 ? launch_avgpool8<3>(xs, B, c_total, c_off, c, ys, ep, st)
+                      : k == 4 ? launch_avgpool8<4>(xs, B, c_total, c_off, c, ys, ep, st) : launch_avgpool8<5>(xs, B, c_total, c_off, c, ys, ep, st);
+        if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return MUPS_ERR_CUDA; }
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         return MUPS_OK;
     }
@@ -651,14 +679,54 @@ int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off
     const long long n = (long long)B * Do * Do * Do * (c / 8);
     const int grid = (int)((n + 255) / 256 < 32 * kNumSMs ? (n + 255) / 256 : 32 * kNumSMs);
     pool3d_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16_dev), B, D, c_total, c_off, c, k,
-                                                                         is_max, static_cast<__nv_bfloat16*>(y_bf16_dev));
+                                                                         is_max, static_cast<__nv_bfloat16*>(y_bf16_dev), ep);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;
 }
 
+int mups_pool3d(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, int is_max, void* y_bf16_dev,
+                mups_stream stream) {
+    return pool_launch("mups_pool3d", x_bf16_dev, B, D, c_total, c_off, c, k, is_max, y_bf16_dev, PoolEpi{nullptr, nullptr, 0, 0, 0}, stream);
+}
+
+int mups_avgpool3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, const float* scale_dev,
+                           const float* shift_dev, int relu, void* y_bf16_dev, int y_total, int y_off, mups_stream stream) {
+    MUPS_REQUIRE(scale_dev && shift_dev, "mups_avgpool3d_bn_relu: NULL scale / shift");
+    MUPS_REQUIRE(k >= 2, "mups_avgpool3d_bn_relu: window %d (a 1-wide pool is the identity: use the convolution's own epilogue)", k);
+    MUPS_REQUIRE(y_total % 8 == 0 && y_off % 8 == 0 && y_off + c <= y_total, "mups_avgpool3d_bn_relu: output channel slice (%d of %d at %d)", c, y_total, y_off);
+    return pool_launch("mups_avgpool3d_bn_relu", x_bf16_dev, B, D, c_total, c_off, c, k, 0, y_bf16_dev,
+                       PoolEpi{scale_dev, shift_dev, relu, y_total, y_off}, stream);
+}
+
+struct ConvSplit { void* y2; int y2_total, y2_off, split, relu_upto; };
+
+static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
+                       int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
+                       int cout_total, int cout_off, float* y_f32_dev, const ConvSplit* sp, mups_stream stream);
+
 int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
                         int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
                         int cout_total, int cout_off, float* y_f32_dev, mups_stream stream) {
+    return conv_launch(x_bf16_dev, B, D, cin_total, cin_off, cin, w_bf16_dev, cin_w, cout, k, scale_dev, shift_dev, relu, y_bf16_dev,
+                       cout_total, cout_off, y_f32_dev, nullptr, stream);
+}
+
+int mups_conv1_split_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
+                             int cin_w, int cout, const float* scale_dev, const float* shift_dev, int relu_upto, void* y1_bf16_dev,
+                             int y1_total, int y1_off, int split, void* y2_bf16_dev, int y2_total, int y2_off, mups_stream stream) {
+    MUPS_REQUIRE(y1_bf16_dev && y2_bf16_dev, "mups_conv1_split_bn_relu: NULL output");
+    MUPS_REQUIRE(split >= 16 && split % 16 == 0 && split < cout && (cout - split) % 16 == 0, "mups_conv1_split_bn_relu: split %d of %d channels", split, cout);
+    MUPS_REQUIRE(y2_total % 8 == 0 && y2_off % 8 == 0 && y2_off + (cout - split) <= y2_total && y1_off + split <= y1_total,
+                 "mups_conv1_split_bn_relu: output channel slices");
+    MUPS_REQUIRE(relu_upto >= 0 && relu_upto <= cout, "mups_conv1_split_bn_relu: relu_upto %d", relu_upto);
+    const ConvSplit sp{y2_bf16_dev, y2_total, y2_off, split, relu_upto};
+    return conv_launch(x_bf16_dev, B, D, cin_total, cin_off, cin, w_bf16_dev, cin_w, cout, 1, scale_dev, shift_dev, relu_upto > 0, y1_bf16_dev,
+                       y1_total, y1_off, nullptr, &sp, stream);
+}
+
+static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
+                       int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
+                       int cout_total, int cout_off, float* y_f32_dev, const ConvSplit* sp, mups_stream stream) {
     MUPS_REQUIRE(x_bf16_dev && w_bf16_dev && scale_dev && shift_dev && (y_bf16_dev || y_f32_dev), "mups_conv3d_bn_relu: NULL buffer");
     MUPS_REQUIRE(B >= 1 && B < (1ll << 30), "mups_conv3d_bn_relu: B=%lld out of range", (long long)B);
     MUPS_REQUIRE(D == 1 || D == 2 || D == 4 || D == 8, "mups_conv3d_bn_relu: volume edge %d (1, 2, 4 or 8)", D);
@@ -667,7 +735,7 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
                  "mups_conv3d_bn_relu: input channels (%d of %d at %d) must be multiples of 8", cin, cin_total, cin_off);
     MUPS_REQUIRE(cin_w >= cin && cin_w % 8 == 0, "mups_conv3d_bn_relu: weight inner dimension %d", cin_w);
     MUPS_REQUIRE(cout >= 16 && cout % 16 == 0, "mups_conv3d_bn_relu: output channels %d must be a multiple of 16", cout);
-    MUPS_REQUIRE(!y_bf16_dev || (cout_total % 8 == 0 && cout_off % 8 == 0 && cout_off + cout <= cout_total),
+    MUPS_REQUIRE(!y_bf16_dev || (cout_total % 8 == 0 && cout_off % 8 == 0 && cout_off + (sp ? sp->split : cout) <= cout_total),
                  "mups_conv3d_bn_relu: output channel slice (%d of %d at %d)", cout, cout_total, cout_off);
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { set_error("mups_conv3d_bn_relu: cuTensorMapEncodeTiled is not available (driver too old?)"); return MUPS_ERR_CUDA; }
@@ -677,7 +745,14 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
     a.kblocks = (cin + kTileK - 1) / kTileK;
     int n_tile = cout;
     if (n_tile > 256) { n_tile = 256; while (cout % n_tile) n_tile -= 16; }
+    if (sp) {                                   // a channel tile must not straddle the two destinations
+        n_tile = sp->split < 256 ? sp->split : 256;
+        while (sp->split % n_tile || (cout - sp->split) % n_tile) n_tile -= 16;
+    }
     a.n_tile = n_tile;
+    a.y2 = sp ? static_cast<__nv_bfloat16*>(sp->y2) : nullptr;
+    a.y2_stride = sp ? sp->y2_total : 0; a.y2_off = sp ? sp->y2_off : 0; a.split = sp ? sp->split : cout;
+    a.relu_upto = sp ? sp->relu_upto : cout;
     const int vox = D * D * D;
     a.dz_box = vox >= kTileM ? kTileM / (D * D) : D;
     a.b_box = vox >= kTileM ? 1 : kTileM / vox;
@@ -777,7 +852,11 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
         return MUPS_OK;
     }
     MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3d_tcgen05_kernel<<<dim3((unsigned)((m_tiles + a.m_sub - 1) / a.m_sub), (unsigned)(cout / n_tile)), kConvThreads, smem,
+    a.n_tiles = cout / n_tile;
+    a.m_ctas = (int)((m_tiles + a.m_sub - 1) / a.m_sub);
+    a.n_fast = getenv("MUPS_CONV_NSLOW") ? 0 : 1;            // benchmarking override: channel tile as the slow index
+    MUPS_REQUIRE(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles <= 0x7FFFFFFFll, "mups_conv3d_bn_relu: grid too large");
+    conv3d_tcgen05_kernel<<<(unsigned)(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles), kConvThreads, smem,
                             static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;

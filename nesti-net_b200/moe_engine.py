@@ -82,6 +82,28 @@ def conv3d_bn_relu(x, cin_off, cin, layer, out=None, cout_off=0, out_f32=None):
     return out if out is not None else out_f32
 
 
+def conv1_split(x, cin_off, cin, layer, split, relu_upto, out1, off1, out2, off2):
+    """``layer``: two 1^3 convolutions stacked along the output channels (rows [0, split) / [split, cout_pad)), one read of x;
+    the first goes to channels [off1, ...) of out1, the second to [off2, ...) of out2 (mups_conv1_split_bn_relu)."""
+    B = int(x.shape[0])
+    D = int(x.shape[1]) if x.ndim == 5 else 1
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mups_conv1_split_bn_relu(
+            _ptr(x), B, D, int(x.shape[-1]), int(cin_off), int(cin), _ptr(layer.w), layer.cin_pad, layer.cout_pad, _ptr(layer.scale),
+            _ptr(layer.shift), int(relu_upto), _ptr(out1), int(out1.shape[-1]), int(off1), int(split), _ptr(out2), int(out2.shape[-1]),
+            int(off2), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mups_conv1_split_bn_relu")
+
+
+def avgpool_bn_relu(x, c_off, c, k, scale, shift, relu, out, y_off):
+    """Average pool (TF 'SAME', window k) of channels [c_off, c_off + c) of x, then act(scale * . + shift) into channels
+    [y_off, y_off + c) of out (mups_avgpool3d_bn_relu)."""
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mups_avgpool3d_bn_relu(
+            _ptr(x), int(x.shape[0]), int(x.shape[1]), int(x.shape[-1]), int(c_off), int(c), int(k), _ptr(scale), _ptr(shift),
+            1 if relu else 0, _ptr(out), int(out.shape[-1]), int(y_off),
+            ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mups_avgpool3d_bn_relu")
+
+
 def pool3d(x, c_off, c, k, is_max):
     """tf_util.avg_pool3d (window k, stride 1, 'SAME': mean over the valid cells) or max_pool3d (2, stride 2) on channels
     [c_off, c_off + c) of the NDHWC bf16 tensor x (mups_pool3d) -> contiguous NDHWC bf16."""
@@ -116,6 +138,26 @@ def _fuse_branches(a, b):
     return f
 
 
+FUSE_POOL_BRANCH = True      # A/B switch (profiles/bench_moe.py): the pool branch's convolution computed with `one`, pooled afterwards
+
+
+def _stack_one_and_pool(one, pool, pool_after):
+    """`one` and the pool branch's 1^3 convolution as one layer (output channels [one | pool]).  pool_after: the average pool
+    runs AFTER this convolution (they commute: both linear, the bias is a constant the valid-cell mean keeps), so the pool half
+    leaves here raw (scale 1, shift 0, no ReLU) and its folded bias + batch norm + ReLU are applied by the pooling kernel."""
+    f = PackedConv.__new__(PackedConv)
+    f.k, f.relu, f.cin_pad = 1, True, one.cin_pad
+    f.cout = f.cout_pad = one.cout_pad + pool.cout_pad
+    f.w = torch.cat([one.w, pool.w], dim=1).contiguous()
+    if pool_after:
+        ident = torch.zeros_like(pool.scale)
+        ident[:pool.cout] = 1.0
+        f.scale, f.shift = torch.cat([one.scale, ident]).contiguous(), torch.cat([one.shift, torch.zeros_like(pool.shift)]).contiguous()
+    else:
+        f.scale, f.shift = torch.cat([one.scale, pool.scale]).contiguous(), torch.cat([one.shift, pool.shift]).contiguous()
+    return f
+
+
 class _PackedInception(object):
     def __init__(self, m, device, in_map=None, cin_pad=None):
         self.k0 = m.k0
@@ -124,6 +166,7 @@ class _PackedInception(object):
         self.a, self.b = mk(m.a), mk(m.b)
         self.nf = self.one.cout_pad
         self.ab = _fuse_branches(self.a, self.b) if (self.a.cout_pad + self.b.cout_pad <= 128 and self.a.k < self.b.k) else None
+        self.one_pool = _stack_one_and_pool(self.one, self.pool, self.k0 > 1)
         self.c_out = 2 * self.nf + self.a.cout_pad + self.b.cout_pad
         # real-channel positions inside this module's (padded) output, for the next layer's weight packing
         real = lambda l, off: [off + i for i in range(l.cout)]
@@ -132,16 +175,25 @@ class _PackedInception(object):
 
     def __call__(self, x, cin_off, cin):
         out = torch.empty(tuple(x.shape[:-1]) + (self.c_out,), dtype=torch.bfloat16, device=x.device)
-        conv3d_bn_relu(x, cin_off, cin, self.one, out, 0)
+        off = self.nf + self.a.cout_pad + self.b.cout_pad
+        fused = FUSE_POOL_BRANCH and self.nf % 16 == 0
+        if fused and self.k0 == 1:               # a 1-wide average pool is the identity: both convolutions, one read of x
+            conv1_split(x, cin_off, cin, self.one_pool, self.nf, 2 * self.nf, out, 0, out, off)
+        elif fused:
+            pre = torch.empty(tuple(x.shape[:-1]) + (self.nf,), dtype=torch.bfloat16, device=x.device)
+            conv1_split(x, cin_off, cin, self.one_pool, self.nf, self.nf, out, 0, pre, 0)
+        else:
+            conv3d_bn_relu(x, cin_off, cin, self.one, out, 0)
         if self.ab is not None:
             conv3d_bn_relu(out, 0, self.nf, self.ab, out, self.nf)
         else:
             conv3d_bn_relu(out, 0, self.nf, self.a, out, self.nf)
             conv3d_bn_relu(out, 0, self.nf, self.b, out, self.nf + self.a.cout_pad)
-        off = self.nf + self.a.cout_pad + self.b.cout_pad
-        if self.k0 == 1:                        # a 1-wide average pool is the identity
+        if fused and self.k0 > 1:
+            avgpool_bn_relu(pre, 0, self.nf, self.k0, self.pool.scale, self.pool.shift, True, out, off)
+        elif not fused and self.k0 == 1:        # a 1-wide average pool is the identity
             conv3d_bn_relu(x, cin_off, cin, self.pool, out, off)
-        else:
+        elif not fused:
             conv3d_bn_relu(pool3d(x, cin_off, cin, self.k0, False), 0, cin, self.pool, out, off)
         return out
 

@@ -86,6 +86,8 @@ def main():
 
 
     # ---- the hand-written tensor-core engine --------------------------------------------------------------------
+    from nesti_net_b200 import moe_engine
+    moe_engine.FUSE_POOL_BRANCH = os.environ.get("FUSE_POOL", "1") != "0"      # A/B: pool branch's convolution fused with `one`
     tc = TensorCoreExperts(net)
     # TC_VARIANTS="pool,conv;..." : mups_set_option pool_variant / conv_variant pairs to A/B (default: the shipped policy)
     variants = [tuple(int(v) for v in pair.split(",")) for pair in os.environ.get("TC_VARIANTS", "0,0").split(";")]
@@ -107,7 +109,7 @@ def main():
         same = (e_s.cpu() == ref_e)
         rms = float(angular_rms_deg(n_s.float().cpu()[same], ref_n[same])) if bool(same.any()) else None
         flops = 6.0e10 * bsz
-        print(json.dumps({"mode": "tcgen05 engine (bf16 x bf16 -> fp32 in TMEM)", "pool_variant": pool_v, "conv_variant": conv_v,
+        print(json.dumps({"mode": "tcgen05 engine (bf16 x bf16 -> fp32 in TMEM)", "pool_variant": pool_v, "conv_variant": conv_v, "fuse_pool_branch": moe_engine.FUSE_POOL_BRANCH,
                           "batch": bsz, "ms_per_batch": round(ms, 2),
                           "queries_per_s": round(bsz / ms * 1e3, 1), "approx_TFLOPs": round(flops / ms / 1e9, 1),
                           "normals_rms_deg_vs_host_fp32": rms, "same_expert": "%d/%d" % (int(same.sum()), n_ref)}), flush=True)
