@@ -1025,6 +1025,44 @@ def test_pool3d_against_tf_semantics(D, k, is_max):
         assert (odd.float() - ref24).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("D,k,nf,cin", [(8, 3, 64, 96), (8, 3, 48, 40), (4, 2, 128, 256), (2, 2, 32, 64), (4, 1, 64, 128)])
+def test_fused_pool_branch_against_the_unfused_layers(D, k, nf, cin):
+    """mups_conv1_split_bn_relu + mups_avgpool3d_bn_relu (the pool branch's 1^3 convolution computed with `one` from one read
+    of the input, the average pool afterwards) against the reference order avg_pool -> conv -> bias + BN -> ReLU in fp32 on
+    the same bf16-rounded operands (models/experts_n_est.py:296-307)."""
+    from nesti_net_b200 import moe_engine as me
+    from nesti_net_b200.experts_net import avg_pool_same
+    torch.manual_seed(D * 7 + k + nf)
+    dev = torch.device("cuda", 0)
+    B = 5
+    x = torch.randn((B, D, D, D, cin + 8), device=dev).to(torch.bfloat16)
+
+    def layer():
+        l = me.PackedConv.__new__(me.PackedConv)
+        l.k, l.relu, l.cout, l.cout_pad, l.cin_pad = 1, True, nf, nf, cin
+        l.w = (torch.randn((1, nf, cin), device=dev) / np.sqrt(cin)).to(torch.bfloat16).contiguous()
+        l.scale, l.shift = torch.rand(nf, device=dev) + 0.5, torch.randn(nf, device=dev) * 0.1
+        return l
+    one, pool = layer(), layer()
+    out = torch.full((B, D, D, D, 2 * nf + 16), 7.0, dtype=torch.bfloat16, device=dev)
+    both = me._stack_one_and_pool(one, pool, k > 1)
+    if k == 1:
+        me.conv1_split(x, 8, cin, both, nf, 2 * nf, out, 0, out, nf + 16)
+    else:
+        pre = torch.empty((B, D, D, D, nf), dtype=torch.bfloat16, device=dev)
+        me.conv1_split(x, 8, cin, both, nf, nf, out, 0, pre, 0)
+        me.avgpool_bn_relu(pre, 0, nf, k, pool.scale, pool.shift, True, out, nf + 16)
+    torch.cuda.synchronize()
+    xs = x[..., 8:].float()
+    ref_one = torch.relu(xs @ one.w[0].float().t() * one.scale + one.shift)
+    pooled = avg_pool_same(xs.permute(0, 4, 1, 2, 3), k).permute(0, 2, 3, 4, 1)
+    ref_pool = torch.relu(pooled @ pool.w[0].float().t() * pool.scale + pool.shift)
+    assert torch.all(out[..., nf:nf + 16] == 7.0), "wrote outside its channel slices"
+    assert (out[..., :nf].float() - ref_one).abs().max().item() < 2e-2 * max(1.0, ref_one.abs().max().item())
+    # the pool half rounds the convolution's output to bf16 before the average: same error level as rounding the pooled input
+    assert (out[..., nf + 16:].float() - ref_pool).abs().max().item() < 2e-2 * max(1.0, ref_pool.abs().max().item())
+
+
 def test_tensor_core_consumer_against_fp32_network():
     """The Mixture-of-Experts forward on the tcgen05 kernels (moe_engine.TensorCoreExperts) against the fp32 PyTorch
     network (experts_net.ExpertsNormalEstimator, TF32 off) on GPU MuPS of a real cloud, batch norm statistics randomised
