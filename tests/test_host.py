@@ -57,6 +57,19 @@ def test_argument_validation_without_compute():
     assert L.mups_set_option(b"stats_variant", 0) == _lib.MUPS_OK
     with pytest.raises(ValueError):
         _lib.check(L.mups_set_option(b"boundary_cap", 100000))
+    # the consumer's entry points validate their channel geometry before touching the device
+    one = ctypes.c_void_p(1)            # non-NULL placeholder: validation fails before any dereference
+    assert L.mups_conv3d_bn_relu(one, 4, 8, 64, 0, 60, one, 64, 64, 3, one, one, 1, one, 64, 0, None, None) == _lib.MUPS_ERR_INVALID
+    assert b"multiples of 8" in L.mups_last_error()
+    assert L.mups_conv3d_bn_relu(one, 4, 3, 64, 0, 64, one, 64, 64, 3, one, one, 1, one, 64, 0, None, None) == _lib.MUPS_ERR_INVALID
+    assert b"volume edge" in L.mups_last_error()
+    assert L.mups_conv1_split_bn_relu(one, 4, 8, 64, 0, 64, one, 64, 128, one, one, 64, one, 64, 0, 40, one, 64, 0, None) == _lib.MUPS_ERR_INVALID
+    assert b"split" in L.mups_last_error()
+    assert L.mups_avgpool3d_bn_relu(one, 4, 8, 64, 0, 64, 1, one, one, 1, one, 64, 0, None) == _lib.MUPS_ERR_INVALID
+    assert b"identity" in L.mups_last_error()
+    assert L.mups_pool3d(one, 4, 8, 64, 0, 64, 3, 1, one, None) == _lib.MUPS_ERR_INVALID        # max pool: window 2 only
+    for name, top in ((b"pool_variant", 1), (b"conv_variant", 5)):
+        assert L.mups_set_option(name, top + 1) == _lib.MUPS_ERR_INVALID and L.mups_set_option(name, 0) == _lib.MUPS_OK
     if not torch.cuda.is_available():
         # no CPU fallback: a valid request fails loudly with MUPS_ERR_CUDA
         assert L.mups_gmm_create(ctypes.byref(h), args(w), args(mu), args(sg), 8) == _lib.MUPS_ERR_CUDA
