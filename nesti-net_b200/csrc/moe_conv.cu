@@ -112,9 +112,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // Epilogue of both convolution kernels: the four epilogue warps read their 32 TMEM lanes x 16 columns at a time, apply
 // scale / shift (+ ReLU), pack to bf16 and store into the channel slice of the NDHWC output (and / or the fp32 output).
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_acc, uint32_t tmem_base, int warp, int lane, int n0, int tile0,
-                                              const int (&tb0)[2], const int (&tz0)[2], uint32_t parity = 0u, int c_lo = 0, int c_hi = 1 << 30) {
+                                              const int (&tb0)[2], const int (&tz0)[2]) {
     // warp w may touch TMEM lanes [32 (w % 4), +32)
-    mbar_wait(bar_acc, parity);
+    mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;                 // row of the tile = voxel in box order (w fastest, then h, z, sample)
@@ -129,7 +129,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_ac
     __nv_bfloat16* yrow = a.y ? (a.y2 && n0 >= a.split ? a.y2 + voxel * a.y2_stride + a.y2_off + (n0 - a.split)
                                                         : a.y + voxel * a.y_stride + a.cout_off + n0) : nullptr;
     float* frow = a.y_f32 ? a.y_f32 + voxel * (long long)a.Cout + n0 : nullptr;
-    for (int c0 = c_lo; c0 < min(a.n_tile, c_hi); c0 += 16) {
+    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(u * a.n_tile + c0), v);
         float f[16];
@@ -260,120 +260,6 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
-// ---- persistent variant for the short-K layers (the 1^3 convolutions: 2-24 stages of work per tile) ------------------------
-// In the kernel above such a layer's epilogue (TMEM -> registers -> 64 KB of stores) is as long as its main loop and nothing
-// overlaps it inside a CTA.  Here one CTA per SM walks over the tiles (channel tile fastest, so that the CTAs reading the same
-// activation tile run together), the producer and the MMA issuer run ahead across tile boundaries through the same
-// shared-memory ring, and the accumulator is DOUBLE-BUFFERED in tensor memory (2 x 256 columns): the epilogue of tile j runs
-// under the loads and MMAs of tile j + 1.  Barriers: acc_full[2] (tcgen05.commit -> epilogue), acc_empty[2] (256 epilogue
-// threads -> MMA issuer); eight epilogue warps, because four cannot drain an accumulator as fast as a 1^3 layer fills one.
-constexpr int kPersistThreads = 320;       // producer warp, MMA warp, EIGHT epilogue warps (two per TMEM lane quarter, half the columns each)
-
-__global__ void __launch_bounds__(kPersistThreads, 1)
-conv3d_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = a.n_tile * kTileK * 2;
-    const int stage_bytes = kABytes + b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);   // full[8], empty[8], acc_full[2], acc_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages), bar_accf = smem_u32(bars + 2 * kMaxStages),
-                   bar_acce = smem_u32(bars + 2 * kMaxStages + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int u = 0; u < 2; ++u) { mbar_init(bar_accf + 8 * u, 1); mbar_init(bar_acce + 8 * u, kPersistThreads - 64); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int tiles_per_sample = (a.D * a.D * a.D + kTileM - 1) / kTileM;          // 4 for 8^3, else 1
-    const int total = a.m_tiles * a.n_tiles;
-    const int taps = a.k * a.k * a.k;
-    const int iters = taps * a.kblocks;
-    auto tile_coords = [&](int t, int& n0, int& tb, int& tz) {
-        const int mt = t / a.n_tiles;
-        n0 = (t - mt * a.n_tiles) * a.n_tile;
-        tb = tiles_per_sample > 1 ? mt / tiles_per_sample : mt * a.b_box;
-        tz = tiles_per_sample > 1 ? (mt % tiles_per_sample) * a.dz_box : 0;
-    };
-
-    if (warp == 0) {
-        if (elect_one()) {
-            int s = 0, ph = 1;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                int n0, tb, tz;
-                tile_coords(t, n0, tb, tz);
-                int tap = 0, kb = 0, dz = 0, dy = 0, dx = 0;
-                for (int it = 0; it < iters; ++it) {
-                    mbar_wait(bar_empty + 8 * s, ph);
-                    const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
-                    mbar_expect_tx(bar_full + 8 * s, (uint32_t)stage_bytes);
-                    tma_load_5d(dst, &map_x, bar_full + 8 * s, kb * kTileK, dx - a.pl, dy - a.pl, tz + dz - a.pl, tb);
-                    tma_load_3d(dst + kABytes, &map_w, bar_full + 8 * s, kb * kTileK, n0, tap);
-                    if (++s == a.stages) { s = 0; ph ^= 1; }
-                    if (++kb == a.kblocks) {
-                        kb = 0; ++tap;
-                        if (++dx == a.k) { dx = 0; if (++dy == a.k) { dy = 0; ++dz; } }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-        int s = 0, ph = 0, j = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-            const int buf = j & 1;
-            mbar_wait(bar_acce + 8 * buf, (uint32_t)(((j >> 1) & 1) ^ 1));       // the epilogue has drained this accumulator
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int it = 0; it < iters; ++it) {
-                mbar_wait(bar_full + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint64_t da = umma_desc(sa), db = umma_desc(sa + kABytes);
-#pragma unroll
-                    for (int k = 0; k < kTileK / 16; ++k)
-                        umma_bf16(tmem_base + (uint32_t)(buf * 256), da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(bar_empty + 8 * s);
-                    if (it == iters - 1) umma_commit(bar_accf + 8 * buf);
-                }
-                __syncwarp();
-                if (++s == a.stages) { s = 0; ph ^= 1; }
-            }
-        }
-    } else {
-        int j = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-            const int buf = j & 1;
-            int n0, tb, tz;
-            tile_coords(t, n0, tb, tz);
-            const int tbs[2] = {tb, 0}, tzs[2] = {tz, 0};
-            const int half = (warp - 2) >> 2, hw = ((a.n_tile >> 1) + 15) & ~15;            // columns [0, hw) / [hw, n_tile)
-            conv_epilogue(a, bar_accf + 8 * buf, tmem_base + (uint32_t)(buf * 256), warp, lane, n0, t / a.n_tiles, tbs, tzs, (uint32_t)((j >> 1) & 1),
-                          half ? hw : 0, half ? a.n_tile : hw);
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acce + 8 * buf) : "memory");
-        }
-    }
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -968,18 +854,6 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     a.n_tiles = cout / n_tile;
     a.m_ctas = (int)((m_tiles + a.m_sub - 1) / a.m_sub);
-    if (iters_total <= 24 && a.m_sub == 1 && m_tiles * a.n_tiles >= 4 * kNumSMs && m_tiles * a.n_tiles <= 0x7FFFFFFFll &&
-        g_conv_variant.load() != 1 && g_conv_variant.load() != 6) {
-        // short K, many tiles: the persistent kernel (double-buffered accumulator; conv_variant 6 = the two-CTAs-per-SM kernel)
-        int st = (int)((200 * 1024) / (kABytes + n_tile * kTileK * 2));
-        a.stages = st > kMaxStages ? kMaxStages : st;
-        const size_t smem_p = (size_t)a.stages * (kABytes + n_tile * kTileK * 2) + 1024 + (2 * kMaxStages + 4) * 8 + 16;
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-        const long long total = m_tiles * a.n_tiles;
-        conv3d_persistent_kernel<<<(unsigned)(total < kNumSMs ? total : kNumSMs), kPersistThreads, smem_p, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
-        MUPS_CHECK_LAUNCH();
-        return MUPS_OK;
-    }
     a.n_fast = getenv("MUPS_CONV_NSLOW") ? 0 : 1;            // benchmarking override: channel tile as the slow index
     MUPS_REQUIRE(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles <= 0x7FFFFFFFll, "mups_conv3d_bn_relu: grid too large");
     conv3d_tcgen05_kernel<<<(unsigned)(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles), kConvThreads, smem,

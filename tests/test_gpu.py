@@ -955,8 +955,7 @@ def _conv_reference(x, cin_off, cin, w, scale, shift, relu, k):
     (2, 1, 1536, 0, 1536, 512, 20), (1, 1, 1536, 0, 1536, 1024, 300), (1, 1, 128, 0, 128, 16, 130), (8, 3, 96, 0, 96, 16, 1),
     (8, 2, 64, 0, 64, 32, 3), (8, 4, 128, 64, 64, 48, 2), (8, 5, 384, 0, 384, 256, 2), (8, 1, 384, 0, 384, 256, 40),
     (8, 3, 256, 0, 256, 128, 3), (8, 5, 136, 8, 128, 128, 2),
-    (8, 3, 128, 0, 128, 128, 600), (8, 4, 64, 0, 64, 128, 593),
-    (8, 1, 128, 0, 128, 128, 160), (8, 1, 72, 8, 64, 512, 80), (4, 1, 256, 0, 256, 256, 1300), (2, 1, 64, 0, 64, 64, 9500)])
+    (8, 3, 128, 0, 128, 128, 600), (8, 4, 64, 0, 64, 128, 593)])
 def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     """mups_conv3d_bn_relu (tcgen05 / TMEM / TMA implicit GEMM, csrc/moe_conv.cu) against torch conv3d in fp32 on the same
     bf16-rounded operands: every volume edge and kernel edge of the reference's networks, 'SAME' padding for even kernels,
@@ -981,16 +980,6 @@ def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     got = out.reshape(-1, cout + 16)
     assert torch.all(got[:, :8] == 7.0) and torch.all(got[:, 8 + cout:] == 7.0), "wrote outside its channel slice"
     assert torch.equal(got[:, 8:8 + cout], f32.to(torch.bfloat16)), "bf16 output is not the rounded fp32 output"
-    if k == 1 and B >= 80:
-        # (>= 592 tiles: the persistent kernel with the double-buffered accumulator; conv_variant 6 = one tile per CTA)
-        _lib.set_option("conv_variant", 6)
-        try:
-            f32b = torch.empty_like(f32)
-            me.conv3d_bn_relu(x, cin_off, cin, layer, None, 0, f32b)
-            torch.cuda.synchronize()
-        finally:
-            _lib.set_option("conv_variant", 0)
-        assert torch.equal(f32b, f32), "persistent and per-tile kernels issue the same MMAs in the same order"
     if D == 8 and k > 1 and cout <= 128:
         # the default above was the z-halo kernel (one activation box per (dy, dx, channel block) serves all dz taps);
         # conv_variant 2 forces the per-tap kernel: same products, another summation order
@@ -1036,9 +1025,8 @@ def test_pool3d_against_tf_semantics(D, k, is_max):
         assert (odd.float() - ref24).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("D,k,nf,cin,B", [(8, 3, 64, 96, 5), (8, 3, 48, 40, 5), (4, 2, 128, 256, 5), (2, 2, 32, 64, 5), (4, 1, 64, 128, 5),
-                                          (8, 3, 128, 64, 160)])
-def test_fused_pool_branch_against_the_unfused_layers(D, k, nf, cin, B):
+@pytest.mark.parametrize("D,k,nf,cin", [(8, 3, 64, 96), (8, 3, 48, 40), (4, 2, 128, 256), (2, 2, 32, 64), (4, 1, 64, 128)])
+def test_fused_pool_branch_against_the_unfused_layers(D, k, nf, cin):
     """mups_conv1_split_bn_relu + mups_avgpool3d_bn_relu (the pool branch's 1^3 convolution computed with `one` from one read
     of the input, the average pool afterwards) against the reference order avg_pool -> conv -> bias + BN -> ReLU in fp32 on
     the same bf16-rounded operands (models/experts_n_est.py:296-307)."""
@@ -1046,6 +1034,7 @@ def test_fused_pool_branch_against_the_unfused_layers(D, k, nf, cin, B):
     from nesti_net_b200.experts_net import avg_pool_same
     torch.manual_seed(D * 7 + k + nf)
     dev = torch.device("cuda", 0)
+    B = 5
     x = torch.randn((B, D, D, D, cin + 8), device=dev).to(torch.bfloat16)
 
     def layer():
