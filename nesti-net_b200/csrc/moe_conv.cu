@@ -100,6 +100,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -129,37 +136,55 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_ac
     __nv_bfloat16* yrow = a.y ? (a.y2 && n0 >= a.split ? a.y2 + voxel * a.y2_stride + a.y2_off + (n0 - a.split)
                                                         : a.y + voxel * a.y_stride + a.cout_off + n0) : nullptr;
     float* frow = a.y_f32 ? a.y_f32 + voxel * (long long)a.Cout + n0 : nullptr;
-    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(u * a.n_tile + c0), v);
-        float f[16];
+    for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
+        // two 16-column TMEM loads in flight before the wait (a 1^3 layer's epilogue is as long as its main loop: its latency
+        // chain -- load, wait, scale / shift fetch, pack, store -- is what bounds those layers)
+        uint32_t v[2][16];
+        const bool second = c0 + 16 < a.n_tile;
+        tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(u * a.n_tile + c0), v[0]);
+        if (second) tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(u * a.n_tile + c0 + 16), v[1]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int co = n0 + c0 + j;
-            const float sc = co < a.Cout ? __ldg(a.scale + co) : 0.f, sh = co < a.Cout ? __ldg(a.shift + co) : 0.f;
-            float t = fmaf(__uint_as_float(v[j]), sc, sh);
-            f[j] = (a.relu && co < a.relu_upto) ? fmaxf(t, 0.f) : t;
-        }
-        if (live) {
-            if (yrow) {
-                uint4 lo, hi;
-                __nv_bfloat162 p;
-                p = __floats2bfloat162_rn(f[0], f[1]);   lo.x = *reinterpret_cast<uint32_t*>(&p);
-                p = __floats2bfloat162_rn(f[2], f[3]);   lo.y = *reinterpret_cast<uint32_t*>(&p);
-                p = __floats2bfloat162_rn(f[4], f[5]);   lo.z = *reinterpret_cast<uint32_t*>(&p);
-                p = __floats2bfloat162_rn(f[6], f[7]);   lo.w = *reinterpret_cast<uint32_t*>(&p);
-                p = __floats2bfloat162_rn(f[8], f[9]);   hi.x = *reinterpret_cast<uint32_t*>(&p);
-                p = __floats2bfloat162_rn(f[10], f[11]); hi.y = *reinterpret_cast<uint32_t*>(&p);
-                p = __floats2bfloat162_rn(f[12], f[13]); hi.z = *reinterpret_cast<uint32_t*>(&p);
-                p = __floats2bfloat162_rn(f[14], f[15]); hi.w = *reinterpret_cast<uint32_t*>(&p);
-                uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
-                dst[0] = lo;
-                dst[1] = hi;
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !second) break;
+            const int cc = c0 + 16 * h;
+            float f[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int co = n0 + cc + 4 * q4;           // n0, cc multiples of 16; scale / shift are padded to Cout (a multiple of 16)
+                float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+                if (co < a.Cout) {
+                    sc = __ldg(reinterpret_cast<const float4*>(a.scale + co));
+                    sh = __ldg(reinterpret_cast<const float4*>(a.shift + co));
+                }
+                const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float t = fmaf(__uint_as_float(v[h][4 * q4 + e]), scv[e], shv[e]);
+                    f[4 * q4 + e] = (a.relu && co + e < a.relu_upto) ? fmaxf(t, 0.f) : t;
+                }
             }
-            if (frow) {
+            if (live) {
+                if (yrow) {
+                    uint4 lo, hi;
+                    __nv_bfloat162 p;
+                    p = __floats2bfloat162_rn(f[0], f[1]);   lo.x = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[2], f[3]);   lo.y = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[4], f[5]);   lo.z = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[6], f[7]);   lo.w = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[8], f[9]);   hi.x = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[10], f[11]); hi.y = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[12], f[13]); hi.z = *reinterpret_cast<uint32_t*>(&p);
+                    p = __floats2bfloat162_rn(f[14], f[15]); hi.w = *reinterpret_cast<uint32_t*>(&p);
+                    uint4* dst = reinterpret_cast<uint4*>(yrow + cc);
+                    dst[0] = lo;
+                    dst[1] = hi;
+                }
+                if (frow) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n0 + c0 + j < a.Cout) frow[c0 + j] = f[j];
+                    for (int e = 0; e < 16; ++e)
+                        if (n0 + cc + e < a.Cout) frow[cc + e] = f[e];
+                }
             }
         }
     }
@@ -737,6 +762,8 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     MUPS_REQUIRE(cout >= 16 && cout % 16 == 0, "mups_conv3d_bn_relu: output channels %d must be a multiple of 16", cout);
     MUPS_REQUIRE(!y_bf16_dev || (cout_total % 8 == 0 && cout_off % 8 == 0 && cout_off + (sp ? sp->split : cout) <= cout_total),
                  "mups_conv3d_bn_relu: output channel slice (%d of %d at %d)", cout, cout_total, cout_off);
+    MUPS_REQUIRE(((reinterpret_cast<uintptr_t>(scale_dev) | reinterpret_cast<uintptr_t>(shift_dev)) & 15) == 0,
+                 "mups_conv3d_bn_relu: scale / shift must be 16-byte aligned");
     EncodeTiledFn enc = encode_tiled();
     if (!enc) { set_error("mups_conv3d_bn_relu: cuTensorMapEncodeTiled is not available (driver too old?)"); return MUPS_ERR_CUDA; }
 
