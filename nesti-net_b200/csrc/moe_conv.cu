@@ -310,15 +310,20 @@ __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_
     const float sc = real ? __ldg(a.scale + co) : 0.f, sh = real ? __ldg(a.shift + co) : 0.f;
     __nv_bfloat16* ycol = a.y ? a.y + voxel0 * a.y_stride + a.cout_off + co : nullptr;
     float* fcol = a.y_f32 ? a.y_f32 + voxel0 * (long long)a.Cout + co : nullptr;
-    for (int j0 = 0; j0 < voxels; j0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)j0, v);
+    for (int j0 = 0; j0 < voxels; j0 += 64) {           // voxels is 256 or 512: four TMEM loads in flight per wait
+        uint32_t v[4][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float t = fmaf(__uint_as_float(v[j]), sc, sh);
-            t = a.relu ? fmaxf(t, 0.f) : t;
-            if (ycol) ycol[(long long)(j0 + j) * a.y_stride] = __float2bfloat16_rn(t);
-            if (fcol && real) fcol[(long long)(j0 + j) * a.Cout] = t;
+        for (int h = 0; h < 4; ++h) tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j0 + 16 * h), v[h]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float t = fmaf(__uint_as_float(v[h][j]), sc, sh);
+                t = a.relu ? fmaxf(t, 0.f) : t;
+                if (ycol) ycol[(long long)(j0 + 16 * h + j) * a.y_stride] = __float2bfloat16_rn(t);
+                if (fcol && real) fcol[(long long)(j0 + 16 * h + j) * a.Cout] = t;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
