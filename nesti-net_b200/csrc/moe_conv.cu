@@ -1,22 +1,26 @@
 // Consumer of the MuPS tensor: the 3D-Inception / Mixture-of-Experts convolutions of
 // models/experts_n_est.py:155-314 (tf_util.conv3d :254-311 and fully_connected :314-351, both with batch norm and ReLU)
-// as ONE hand-written implicit-GEMM kernel on the 5th-generation tensor cores:
+// as hand-written implicit GEMMs on the 5th-generation tensor cores:
 //
 //   y[b, z, y, x, co] = act( scale[co] * sum_{dz,dy,dx,ci} x[b, z+dz-p, y+dy-p, x+dx-p, ci] * w[dz,dy,dx][co][ci] + shift[co] )
 //
-// * GEMM view: M = voxels (tile of 128 = two z-slices of an 8^3 volume, two whole 4^3 volumes, sixteen 2^3 volumes or 128
-//   flattened rows of a fully connected layer), N = output channels (tile <= 256), K = taps x input channels (64 per stage).
-// * A operand: one TMA load per (tap, 64-channel block) of the NDHWC bf16 activations through a 5-D tiled tensor map whose box
-//   is (64 channels, W, H, dz-box, batch-box); the tap only shifts the box coordinates and the TMA unit zero-fills what falls
-//   outside the volume -- TF 'SAME' padding (asymmetric for even kernels: the smaller half first) without an im2col buffer
-//   and without a single predicate.  The box lands in shared memory as 128 rows of 128 bytes in the 128-byte-swizzled K-major
-//   layout tcgen05.mma reads.
-// * B operand: weights [tap][Cout][Cin] bf16 through a 3-D tensor map, same layout.
-// * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one elected thread, accumulator in tensor memory (128 lanes x N
-//   columns), tcgen05.commit arrives on the mbarriers that free the shared-memory stage / announce the finished accumulator.
-// * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (tcgen05.ld 32 lanes x 32 columns each, folded
-//   bias + batch norm as scale / shift, ReLU, bf16 pack, 16-byte stores into a channel slice of the NDHWC output, so the
-//   inception module's concat costs nothing).
+// * GEMM view: voxels x output channels x (taps x input channels, 64 per stage).
+// * Activations: TMA loads of the NDHWC bf16 tensor through a 5-D tiled tensor map whose box is (64 channels, W, H, z-slices,
+//   samples); a tap only shifts the box coordinates and the TMA unit zero-fills what falls outside the volume -- TF 'SAME'
+//   padding (asymmetric for even kernels: the smaller half first) without an im2col buffer and without a single predicate.
+//   The box lands in shared memory as rows of 128 bytes in the 128-byte-swizzled K-major layout tcgen05.mma reads.
+// * Weights [tap][Cout][Cin] bf16 through a 3-D tensor map, same layout.
+// * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) issued by one elected thread, accumulators in tensor memory, tcgen05.commit
+//   arrives on the mbarriers that free the shared-memory stages / announce the finished accumulator.
+// * warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (tcgen05.ld, folded bias + batch norm as scale /
+//   shift, ReLU, bf16 pack, stores into a channel slice of the NDHWC output, so the inception module's concat costs nothing).
+// Kernels:
+//   conv3d_tcgen05_kernel   one 128-voxel activation tile (two when N <= 128) + one weight tile per (tap, channel block):
+//                           the 1^3 layers (two CTAs per SM), the 4^3 / 2^3 volumes, the fully connected layers
+//   conv3d_zhalo_kernel     the 8^3 volumes with k > 1 (85 % of the arithmetic): one activation box per (dy, dx, channel
+//                           block) serves all k dz-taps; 128-channel tiles with the operand roles swapped (weights = M,
+//                           voxels = N = 256), out-of-volume slices left out of the MMAs, whole sample per CTA for large batches
+//   avgpool8_tile_kernel, maxpool2_kernel, pool3d_kernel, pack_mups_bf16_kernel: the pools and the input conversion
 // Every mbarrier wait is bounded: a barrier that never completes traps instead of hanging the GPU.
 #include <cstdlib>
 
