@@ -85,7 +85,8 @@ int64_t mups_launch_count(void);
  * "pool_variant" (0 = automatic: shared-memory tile + separable box sum for the 8^3 average pools; 1 = the per-voxel
  * kernel everywhere) and "conv_variant" (0 = automatic; 1 = one CTA per SM with the deepest pipeline also for the short-K 1^3
  * layers; 2 = the per-tap kernel also for the 8^3 layers; 3 = z-halo kernel without the operand swap; 4 = half-sample CTAs
- * at every batch size): benchmarking only. */
+ * at every batch size; 5 = no channel-tile splitting for nearly empty grids; 7 = two voxel tiles per 256-channel tile in the 1^3
+ * layers): benchmarking only. */
 int mups_set_option(const char* name, int64_t value);
 
 /* ---- spatial index (K1 bbox + K2 grid build) --------------------------------------------- */

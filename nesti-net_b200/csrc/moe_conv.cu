@@ -207,6 +207,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);      // full[stages], empty[stages], accumulator
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages), bar_acc = smem_u32(bars + 2 * kMaxStages);
+    const uint32_t tmem_cols = a.m_sub * a.n_tile > kTmemCols ? 512u : (uint32_t)kTmemCols;   // two 256-channel accumulators: all of TMEM
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -219,7 +220,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -288,7 +289,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -801,6 +802,10 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     // two voxel tiles per CTA share one weight tile when both accumulators fit the 256 TMEM columns and the layer is deep
     // enough for operand delivery to matter (g_conv_m_sub: benchmarking override)
     a.m_sub = (n_tile <= 128 && m_tiles >= 2 * kNumSMs && k > 1) ? 2 : 1;
+    // conv_variant 7 (experiment): 1^3 layers with 256-channel tiles take two voxel tiles per CTA (all 512 TMEM columns, one CTA per
+    // SM): a third less L2 -> SM traffic per output (the weight tile is streamed once per 256 voxels), no epilogue overlap
+    const bool wide1 = k == 1 && n_tile == 256 && m_tiles >= 4 * kNumSMs && g_conv_variant.load() == 7;
+    if (wide1) a.m_sub = 2;
     if (k > 1 && D < 8 && ((m_tiles + a.m_sub - 1) / a.m_sub) * (cout / n_tile) < kNumSMs / 4 && g_conv_variant.load() != 5) {
         // nearly empty grids (a 2^3 layer of a 256-query batch is 16 tiles -- 16 CTAs on 148 SMs; measured: +2.5 % on the whole
         // forward at batch 256, while splitting grids of 64 or more CTAs gains nothing -- their K loop is latency-bound).  Pick the
@@ -830,7 +835,7 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     // inside one CTA, so leave room for TWO CTAs per SM (<= 100 KB of shared memory and 256 TMEM columns each) -- one CTA's
     // epilogue then runs under the other's loads and MMAs
     const int iters_total = k * k * k * a.kblocks;
-    if (iters_total <= 24 && m_tiles > kNumSMs && g_conv_variant.load() != 1) stages = (100 * 1024) / stage_bytes < 2 ? 2 : (100 * 1024) / stage_bytes;
+    if (iters_total <= 24 && m_tiles > kNumSMs && g_conv_variant.load() != 1 && !wide1) stages = (100 * 1024) / stage_bytes < 2 ? 2 : (100 * 1024) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > iters_total) stages = iters_total < 2 ? 2 : iters_total;
     a.stages = stages;
