@@ -293,6 +293,115 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
 }
 
+// ---- CTA-pair variant for the 1^3 layers -----------------------------------------------------------------------------------
+// Those layers are bound by L2 -> SM traffic: every 128-voxel tile streams the layer's whole weight matrix again (two thirds
+// of the bytes).  Here a thread-block CLUSTER of two CTAs works on two voxel tiles and ONE channel tile: each CTA loads half
+// of every weight tile and the TMA unit multicasts it into both shared memories (.multicast::cluster), so a CTA fetches
+// 16 KB of activations + half a weight tile per stage instead of a whole one.  A stage may be refilled once BOTH CTAs' MMAs have read
+// it: the empty barriers count two arrivals, tcgen05.commit arrives on the peer's barrier too (.multicast::cluster).  The two
+// CTAs stay ordinary 100 KB CTAs, so two of them still share an SM and overlap their epilogues.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3d_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w_half, const ConvArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.n_tile * kTileK * 2, half_bytes = b_bytes / 2;
+    const int stage_bytes = kABytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);      // full[stages], empty[stages], accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages), bar_acc = smem_u32(bars + 2 * kMaxStages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_half) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < a.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                 // the peer's barriers exist before anything is multicast into this CTA
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // grid: channel tile slow, voxel tile fast, so that a cluster = two consecutive voxel tiles of one channel tile
+    const int n0 = (int)(blockIdx.x / (unsigned)a.m_ctas) * a.n_tile;
+    const int tiles_per_sample = (a.D * a.D * a.D + kTileM - 1) / kTileM;
+    const int tile0 = (int)(blockIdx.x % (unsigned)a.m_ctas);
+    const int tb0[2] = {tiles_per_sample > 1 ? tile0 / tiles_per_sample : tile0 * a.b_box, 0};
+    const int tz0[2] = {tiles_per_sample > 1 ? (tile0 % tiles_per_sample) * a.dz_box : 0, 0};
+    const int taps = a.k * a.k * a.k;
+    const int iters = taps * a.kblocks;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int s = 0, ph = 1, tap = 0, kb = 0, dz = 0, dy = 0, dx = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(bar_empty + 8 * s, ph);                          // both CTAs have read this stage
+                const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_expect_tx(bar_full + 8 * s, (uint32_t)stage_bytes);   // own activations + both halves of the weight tile
+                tma_load_5d(dst, &map_x, bar_full + 8 * s, kb * kTileK, dx - a.pl, dy - a.pl, tz0[0] + dz - a.pl, tb0[0]);
+                tma_load_3d_multicast(dst + kABytes + rank * half_bytes, &map_w_half, bar_full + 8 * s, kb * kTileK,
+                                      n0 + (int)rank * (a.n_tile / 2), tap, (uint16_t)3);
+                if (++s == a.stages) { s = 0; ph ^= 1; }
+                if (++kb == a.kblocks) {
+                    kb = 0; ++tap;
+                    if (++dx == a.k) { dx = 0; if (++dy == a.k) { dy = 0; ++dz; } }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        int s = 0, ph = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(bar_full + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t da = umma_desc(sa), db = umma_desc(sa + kABytes);
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k)
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                umma_commit_multicast(bar_empty + 8 * s, (uint16_t)3);     // frees the stage in BOTH CTAs (each refills half of it)
+                if (it == iters - 1) umma_commit(bar_acc);
+            }
+            __syncwarp();
+            if (++s == a.stages) { s = 0; ph ^= 1; }
+        }
+    } else {
+        conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
+    }
+    __syncthreads();
+    cluster_sync_all();                 // nobody leaves while the peer may still write into this CTA's shared memory / barriers
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ---- z-halo variant for the 8^3 volumes (the layers that carry 85 % of the network's arithmetic) -----------------------------
 // The kernel above re-reads the activation tile from L2 once per tap and sits at the L2 -> SM throughput cap.  A shift of
 // the window by one z-slice is a shift by 64 rows = 8 swizzle atoms of the K-major shared-memory tile, i.e. a LEGAL operand
@@ -786,6 +895,10 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
         n_tile = sp->split < 256 ? sp->split : 256;
         while (sp->split % n_tile || (cout - sp->split) % n_tile) n_tile -= 16;
     }
+    if (const char* e = getenv("MUPS_CONV_N1")) {          // experiment: narrower channel tiles (deeper pipelines) for the 1^3 layers
+        const int want = atoi(e);
+        if (k == 1 && D > 1 && want >= 16 && want < n_tile && n_tile % want == 0 && (!sp || sp->split % want == 0)) n_tile = want;
+    }
     a.n_tile = n_tile;
     a.y2 = sp ? static_cast<__nv_bfloat16*>(sp->y2) : nullptr;
     a.y2_stride = sp ? sp->y2_total : 0; a.y2_off = sp ? sp->y2_off : 0; a.split = sp ? sp->split : cout;
@@ -895,6 +1008,32 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     a.n_tiles = cout / n_tile;
     a.m_ctas = (int)((m_tiles + a.m_sub - 1) / a.m_sub);
+    if (k == 1 && a.m_sub == 1 && n_tile >= 32 && n_tile % 32 == 0 && m_tiles >= 4 * kNumSMs && g_conv_variant.load() == 8) {
+        // CTA pairs sharing the weight tile by TMA multicast (see conv3d_pair_kernel)
+        CUtensorMap map_wh;
+        const cuuint64_t dims[3] = {(cuuint64_t)cin_w, (cuuint64_t)cout, (cuuint64_t)(k * k * k)};
+        const cuuint64_t strides[2] = {(cuuint64_t)cin_w * 2, (cuuint64_t)cin_w * 2 * cout};
+        const cuuint32_t box[3] = {(cuuint32_t)kTileK, (cuuint32_t)(n_tile / 2), 1};
+        const cuuint32_t es[3] = {1, 1, 1};
+        const CUresult r = enc(&map_wh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16_dev), dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("mups_conv3d_bn_relu: half weight tensor map rejected (CUresult %d)", (int)r); return MUPS_ERR_CUDA; }
+        a.m_ctas = (a.m_ctas + 1) & ~1;                      // an odd tail tile gets an all-out-of-bounds partner
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((long long)a.m_ctas * a.n_tiles));
+        cfg.blockDim = dim3(kConvThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        MUPS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3d_pair_kernel, map_x, map_wh, a));
+        MUPS_CHECK_LAUNCH();
+        return MUPS_OK;
+    }
     a.n_fast = getenv("MUPS_CONV_NSLOW") ? 0 : 1;            // benchmarking override: channel tile as the slow index
     MUPS_REQUIRE(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles <= 0x7FFFFFFFll, "mups_conv3d_bn_relu: grid too large");
     conv3d_tcgen05_kernel<<<(unsigned)(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles), kConvThreads, smem,

@@ -68,7 +68,7 @@ def test_argument_validation_without_compute():
     assert L.mups_avgpool3d_bn_relu(one, 4, 8, 64, 0, 64, 1, one, one, 1, one, 64, 0, None) == _lib.MUPS_ERR_INVALID
     assert b"identity" in L.mups_last_error()
     assert L.mups_pool3d(one, 4, 8, 64, 0, 64, 3, 1, one, None) == _lib.MUPS_ERR_INVALID        # max pool: window 2 only
-    for name, top in ((b"pool_variant", 1), (b"conv_variant", 5)):
+    for name, top in ((b"pool_variant", 1), (b"conv_variant", 8)):
         assert L.mups_set_option(name, top + 1) == _lib.MUPS_ERR_INVALID and L.mups_set_option(name, 0) == _lib.MUPS_OK
     if not torch.cuda.is_available():
         # no CPU fallback: a valid request fails loudly with MUPS_ERR_CUDA
