@@ -201,6 +201,22 @@ int mups_conv1_split_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_t
 int mups_avgpool3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int c, int k, const float* scale_dev,
                            const float* shift_dev, int relu, void* y_bf16_dev, int y_total, int y_off, mups_stream stream);
 
+/* ---- bf16x3 ("split") mode of the consumer: fp32-grade results from the same tensor-core kernels ------------------------
+ * A value is carried as hi = bf16(v), lo = bf16(v - hi); a tensor of w logical channels is stored as the TRIPLET
+ * [hi | lo | hi] (3 w channels), the weights are expanded to [w_hi | w_hi | w_lo], and mups_conv3d_bn_relu over the 3 x longer
+ * channel axis accumulates a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32 (writing its y_f32_dev output).  The two entry points
+ * below turn fp32 back into triplets; they replace nothing in the reference (which computes in fp32 throughout,
+ * models/experts_n_est.py:155-314) -- they are what lets the bf16 tensor cores reproduce it to ~1e-5 relative. */
+/* fp32 src_dev [rows, src_stride], columns [src_off, src_off + w_src) -> triplet at channels [dst_off, dst_off + 3 w_dst) of
+ * dst_bf16_dev [rows, dst_stride] (w_dst >= w_src, a multiple of 8; channels [w_src, w_dst) of every part are zero). */
+int mups_split_bf16x3(const float* src_dev, int64_t rows, int src_stride, int src_off, int w_src, void* dst_bf16_dev, int dst_stride,
+                      int dst_off, int w_dst, mups_stream stream);
+/* tf_util.avg_pool3d / max_pool3d (as mups_pool3d) from the triplet at channels [c_off, c_off + 3 w) of x_bf16_dev
+ * [B, D, D, D, c_total] to the triplet at [y_off, y_off + 3 w) of y_bf16_dev [B, D', D', D', y_total]; the window is
+ * reduced on hi + lo in fp32. */
+int mups_pool3d_bf16x3(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int w, int k, int is_max, void* y_bf16_dev,
+                       int y_total, int y_off, mups_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,12 @@ NDHWC kernel (``mups_pool3d``); torch is left with the softmax over seven gate o
 Precision: bf16 products, fp32 sums.  The normals stay within a few tenths of a degree of the fp32 network
 (tests/test_gpu.py::test_tensor_core_consumer_against_fp32_network states the measured deviation); that is two orders of
 magnitude below the 5 / 10 degree thresholds of the reference's own metrics (utils/evaluate.py: PGP5, PGP10).
+
+``TensorCoreExperts(model, precision="bf16x3")`` is the fp32-grade mode for callers who want the reference's fp32 numbers from
+the tensor cores: every value is carried as two bf16 numbers (hi, lo), a tensor of w logical channels is stored as the
+triplet [hi | lo | hi], the weights are expanded to [w_hi | w_hi | w_lo], and the SAME convolution kernel over the three
+times longer channel axis accumulates a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32 (csrc/moe_split.cu).  Three times the
+tensor-core work, 16 significant bits per operand instead of 8.
 """
 import ctypes
 
@@ -40,9 +46,10 @@ class PackedConv(object):
     eps 1e-3) and bias folded: weights [k^3][Cout_pad][Cin_pad] bf16 (tap order dz, dy, dx; TF cross-correlation), scale /
     shift [Cout_pad] fp32."""
 
-    def __init__(self, weight, bias, bn, relu, k, device, in_map=None, cin_pad=None):
+    def __init__(self, weight, bias, bn, relu, k, device, in_map=None, cin_pad=None, x3_segs=None):
         """weight: [Cout, Cin, k, k, k] (conv) or [Cout, Cin] (linear); in_map: for each real input channel its index in
-        the padded input layout (None: identity)."""
+        the padded input layout (None: identity).  x3_segs (bf16x3 mode): the widths of the input layout's segments, each of
+        which is stored as a triplet [hi | lo | hi]; the weights' inner axis becomes [w_hi | w_hi | w_lo] per segment."""
         w = weight.detach().float().cpu()
         if w.ndim == 2:
             w = w[:, :, None, None, None]
@@ -61,6 +68,17 @@ class PackedConv(object):
             s, t = torch.ones(cout), b
         scale, shift = torch.zeros(self.cout_pad), torch.zeros(self.cout_pad)
         scale[:cout], shift[:cout] = s, t
+        if x3_segs is not None:
+            if sum(x3_segs) != self.cin_pad:
+                raise ValueError("bf16x3 segments %r do not cover the %d input channels" % (list(x3_segs), self.cin_pad))
+            w_hi = wp.to(torch.bfloat16).float()
+            w_lo = wp - w_hi                                  # exact in fp32; rounded to bf16 below
+            parts, s0 = [], 0
+            for wd in x3_segs:
+                parts += [w_hi[..., s0:s0 + wd], w_hi[..., s0:s0 + wd], w_lo[..., s0:s0 + wd]]
+                s0 += wd
+            wp = torch.cat(parts, dim=-1)
+            self.cin_pad *= 3
         self.w = wp.to(device=device, dtype=torch.bfloat16).contiguous()
         self.scale = scale.to(device).contiguous()
         self.shift = shift.to(device).contiguous()
@@ -113,6 +131,45 @@ def pool3d(x, c_off, c, k, is_max):
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().mups_pool3d(_ptr(x), B, D, int(x.shape[-1]), int(c_off), int(c), int(k), 1 if is_max else 0, _ptr(y),
                                            ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mups_pool3d")
+    return y
+
+
+def conv3d_f32(x, cin_off, cin, layer):
+    """The same convolution with its fp32 output only: [rows, Cout_pad] (scale / shift / ReLU applied)."""
+    rows = x.numel() // int(x.shape[-1])
+    out = torch.empty((rows, layer.cout_pad), dtype=torch.float32, device=x.device)
+    conv3d_bn_relu(x, cin_off, cin, layer, None, 0, out)
+    return out
+
+
+def split_x3(src, src_off, w_src, dst, dst_off, w_dst):
+    """fp32 src [rows, n] columns [src_off, src_off + w_src) -> the triplet [hi | lo | hi] at channels [dst_off, dst_off + 3 w_dst)
+    of the bf16 tensor dst [..., Ct] (mups_split_bf16x3)."""
+    rows = dst.numel() // int(dst.shape[-1])
+    with torch.cuda.device(dst.device):
+        _lib.check(_lib.load().mups_split_bf16x3(_ptr(src), rows, int(src.shape[-1]), int(src_off), int(w_src), _ptr(dst), int(dst.shape[-1]),
+                                                 int(dst_off), int(w_dst), ctypes.c_void_p(torch.cuda.current_stream(dst.device).cuda_stream)),
+                   "mups_split_bf16x3")
+
+
+def pool3d_x3(x, c_off, w, k, is_max, y, y_off):
+    """Average / max pool (as pool3d) of the triplet at channels [c_off, c_off + 3 w) of x into the triplet at y_off of y."""
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mups_pool3d_bf16x3(_ptr(x), int(x.shape[0]), int(x.shape[1]), int(x.shape[-1]), int(c_off), int(w), int(k),
+                                                  1 if is_max else 0, _ptr(y), int(y.shape[-1]), int(y_off),
+                                                  ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mups_pool3d_bf16x3")
+
+
+def _pool_segments_x3(x, c_off, segs, k, is_max):
+    """Pool the logical channels [c_off, c_off + sum(segs)) of a triplet tensor segment by segment -> a new triplet tensor with
+    the same segments."""
+    B, D = int(x.shape[0]), int(x.shape[1])
+    Do = D // 2 if is_max else D
+    y = torch.empty((B, Do, Do, Do, 3 * sum(segs)), dtype=torch.bfloat16, device=x.device)
+    s0 = 0
+    for wd in segs:
+        pool3d_x3(x, 3 * (c_off + s0), wd, k, is_max, y, 3 * s0)
+        s0 += wd
     return y
 
 
@@ -198,29 +255,71 @@ class _PackedInception(object):
         return out
 
 
-class _PackedConvNet(object):
-    def __init__(self, net, device, in_map, cin_pad):
-        self.steps = []
-        it = iter(net.mods)
-        cur_map, cur_pad = in_map, cin_pad
-        for step in net.plan:
-            if step is None:
-                inc = _PackedInception(next(it), device, cur_map, cur_pad)
-                self.steps.append(inc)
-                cur_map, cur_pad = inc.out_map, inc.c_out
-            else:
-                self.steps.append(step)
-        self.out_map, self.out_pad = cur_map, cur_pad
+class _PackedInceptionX3(object):
+    """The inception module in bf16x3 mode: the module's output holds the triplets of its four branches
+    [one | a | b | pool] one after the other; every convolution leaves through its fp32 output and split_x3."""
+
+    def __init__(self, m, device, in_map, cin_pad, in_segs):
+        self.k0, self.in_segs = m.k0, list(in_segs)
+        mk = lambda c, im, cp, sg: PackedConv(c.conv.weight, c.conv.bias, c.bn, True, c.conv.kernel_size[0], device, im, cp, sg)
+        self.one, self.pool = mk(m.one, in_map, cin_pad, in_segs), mk(m.pool, in_map, cin_pad, in_segs)
+        self.nf = self.one.cout_pad
+        self.a, self.b = mk(m.a, None, self.nf, [self.nf]), mk(m.b, None, self.nf, [self.nf])
+        self.ab = _fuse_branches(self.a, self.b) if (self.a.cout_pad + self.b.cout_pad <= 128 and self.a.k < self.b.k) else None
+        self.c_out = 2 * self.nf + self.a.cout_pad + self.b.cout_pad
+        self.out_segs = [self.nf, self.a.cout_pad, self.b.cout_pad, self.nf]
+        real = lambda l, off: [off + i for i in range(l.cout)]
+        self.out_map = (real(self.one, 0) + real(self.a, self.nf) + real(self.b, self.nf + self.a.cout_pad)
+                        + real(self.pool, self.nf + self.a.cout_pad + self.b.cout_pad))
 
     def __call__(self, x, cin_off, cin):
-        for step in self.steps:
-            if isinstance(step, _PackedInception):
-                x = step(x, cin_off, cin)
-                cin_off, cin = 0, int(x.shape[-1])
+        """x: triplet tensor; cin_off, cin: LOGICAL channels (whole segments)."""
+        out = torch.empty(tuple(x.shape[:-1]) + (3 * self.c_out,), dtype=torch.bfloat16, device=x.device)
+        nf, ap, bp = self.nf, self.a.cout_pad, self.b.cout_pad
+        split_x3(conv3d_f32(x, 3 * cin_off, 3 * cin, self.one), 0, nf, out, 0, nf)
+        if self.ab is not None:
+            t = conv3d_f32(out, 0, 3 * nf, self.ab)
+            split_x3(t, 0, ap, out, 3 * nf, ap)
+            split_x3(t, ap, bp, out, 3 * (nf + ap), bp)
+        else:
+            split_x3(conv3d_f32(out, 0, 3 * nf, self.a), 0, ap, out, 3 * nf, ap)
+            split_x3(conv3d_f32(out, 0, 3 * nf, self.b), 0, bp, out, 3 * (nf + ap), bp)
+        if self.k0 == 1:                         # a 1-wide average pool is the identity
+            t = conv3d_f32(x, 3 * cin_off, 3 * cin, self.pool)
+        else:
+            t = conv3d_f32(_pool_segments_x3(x, cin_off, self.in_segs, self.k0, False), 0, 3 * cin, self.pool)
+        split_x3(t, 0, nf, out, 3 * (nf + ap + bp), nf)
+        return out
+
+
+class _PackedConvNet(object):
+    def __init__(self, net, device, in_map, cin_pad, x3_segs=None):
+        """x3_segs: None (bf16 activations) or the segment widths of the input slice (bf16x3 mode, triplet tensors)."""
+        self.steps, self.x3 = [], x3_segs is not None
+        it = iter(net.mods)
+        cur_map, cur_pad, cur_segs = in_map, cin_pad, (list(x3_segs) if self.x3 else None)
+        for step in net.plan:
+            if step is None:
+                inc = (_PackedInceptionX3(next(it), device, cur_map, cur_pad, cur_segs) if self.x3
+                       else _PackedInception(next(it), device, cur_map, cur_pad))
+                self.steps.append(inc)
+                cur_map, cur_pad = inc.out_map, inc.c_out
+                cur_segs = inc.out_segs if self.x3 else None
             else:
+                self.steps.append((step, cur_segs))
+        self.out_map, self.out_pad, self.out_segs = cur_map, cur_pad, cur_segs
+
+    def __call__(self, x, cin_off, cin):
+        """cin_off, cin: channels of x the first module reads (LOGICAL channels in bf16x3 mode)."""
+        for step in self.steps:
+            if isinstance(step, (_PackedInception, _PackedInceptionX3)):
+                x = step(x, cin_off, cin)
+                cin_off, cin = 0, step.c_out
+            else:
+                (step, segs) = step
                 if (step[1], step[2]) != (2, 2) or x.shape[1] % 2:
                     raise ValueError("only the 2-wide, stride-2 max pools of the reference's 8^3 networks are packed")
-                x = pool3d(x, 0, int(x.shape[-1]), 2, True)
+                x = _pool_segments_x3(x, 0, segs, 2, True) if self.x3 else pool3d(x, 0, int(x.shape[-1]), 2, True)
         if x.shape[1] != 1:
             raise ValueError("only the 8^3 networks of the reference (which end at a 1^3 volume) are packed for the tensor cores")
         return x.reshape(x.shape[0], -1)       # TF flattens channels-last [B, d, h, w, C]
@@ -231,9 +330,12 @@ class TensorCoreExperts(object):
     [B, res, res, res, 20 S] on the GPU and returns (normal of the most probable expert [B, 3], expert [B],
     probabilities [B, n_experts]) like ``ExpertsNormalEstimator.predict``."""
 
-    def __init__(self, model, device=None):
+    def __init__(self, model, device=None, precision="bf16"):
         if not torch.cuda.is_available():
             raise RuntimeError("TensorCoreExperts needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3', not %r" % (precision,))
+        self.precision, self.x3 = precision, precision == "bf16x3"
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         model = model.eval()
         self.expert_dict = model.expert_dict
@@ -241,35 +343,49 @@ class TensorCoreExperts(object):
         self.n_rads = int(first.in_channels) // 20
         S = self.n_rads
         scale_map = lambda scales: [32 * i + c for i in range(len(scales)) for c in range(20)]      # 20 real channels per 32-wide scale slot
-        self.gate = _PackedConvNet(model.gate_conv, self.device, scale_map(range(S)), 32 * S)
+        segs = lambda scales: [32] * len(scales) if self.x3 else None                               # bf16x3: one triplet per scale slot
+        self.gate = _PackedConvNet(model.gate_conv, self.device, scale_map(range(S)), 32 * S, segs(range(S)))
         self.gate_fc = self._pack_fc(model.gate_fc, self.gate)
         self.experts = []
         for i, (conv, fc) in enumerate(zip(model.expert_conv, model.expert_fc)):
             scales = self.expert_dict[i]
-            net = _PackedConvNet(conv, self.device, scale_map(scales), 32 * len(scales))
+            net = _PackedConvNet(conv, self.device, scale_map(scales), 32 * len(scales), segs(scales))
             self.experts.append((int(np.min(scales)) * 32, 32 * len(scales), net, self._pack_fc(fc, net)))
         self.n_experts = len(self.experts)
 
     def _pack_fc(self, seq, net):
-        layers, in_map, pad = [], net.out_map, net.out_pad
+        layers, in_map, pad, sg = [], net.out_map, net.out_pad, net.out_segs
         for fc in seq:
-            l = PackedConv(fc.lin.weight, fc.lin.bias, fc.bn, fc.relu, 1, self.device, in_map, pad)
+            l = PackedConv(fc.lin.weight, fc.lin.bias, fc.bn, fc.relu, 1, self.device, in_map, pad, sg)
             layers.append(l)
             in_map, pad = None, l.cout_pad
+            sg = [l.cout_pad] if self.x3 else None
         return layers
 
     def _run_fc(self, layers, x):
         for l in layers[:-1]:
-            x = conv3d_bn_relu(x, 0, int(x.shape[-1]), l)
+            if self.x3:
+                t = conv3d_f32(x, 0, int(x.shape[-1]), l)
+                x = torch.empty((x.shape[0], 3 * l.cout_pad), dtype=torch.bfloat16, device=x.device)
+                split_x3(t, 0, l.cout_pad, x, 0, l.cout_pad)
+            else:
+                x = conv3d_bn_relu(x, 0, int(x.shape[-1]), l)
         last = layers[-1]
         out = torch.empty((x.shape[0], last.cout_pad), dtype=torch.float32, device=x.device)
         conv3d_bn_relu(x, 0, int(x.shape[-1]), last, None, 0, out)
         return out[:, :last.cout]
 
     def pack_input(self, mups):
-        """fp32 MuPS [B, res, res, res, 20 S] -> bf16 [B, res, res, res, 32 S] (every scale padded to 32 channels)."""
+        """fp32 MuPS [B, res, res, res, 20 S] -> bf16 [B, res, res, res, 32 S] (every scale padded to 32 channels); in bf16x3
+        mode [B, res, res, res, 96 S]: one triplet [hi | lo | hi] of 32-wide parts per scale."""
         B, res = int(mups.shape[0]), int(mups.shape[1])
         S = self.n_rads
+        if self.x3:
+            x = torch.empty((B, res, res, res, 96 * S), dtype=torch.bfloat16, device=mups.device)
+            src = mups.reshape(B * res ** 3, 20 * S)
+            for s in range(S):
+                split_x3(src, 20 * s, 20, x, 96 * s, 32)
+            return x
         x = torch.empty((B, res, res, res, 32 * S), dtype=torch.bfloat16, device=mups.device)
         with torch.cuda.device(mups.device):
             _lib.check(_lib.load().mups_moe_pack_input(_ptr(mups), B * res ** 3, S, _ptr(x),
@@ -282,7 +398,7 @@ class TensorCoreExperts(object):
         """(experts_prob [n_experts, B], n_est [n_experts, B, 3]) like ExpertsNormalEstimator.forward."""
         mups = mups.to(self.device, torch.float32).contiguous()
         x = self.pack_input(mups)
-        logits = self._run_fc(self.gate_fc, self.gate(x, 0, int(x.shape[-1])))
+        logits = self._run_fc(self.gate_fc, self.gate(x, 0, 32 * self.n_rads))
         prob = F.softmax(logits, dim=1).transpose(0, 1)
         normals = [self._run_fc(fc, net(x, off, width)) for off, width, net, fc in self.experts]
         return prob, torch.stack(normals)

@@ -114,6 +114,31 @@ def main():
                           "queries_per_s": round(bsz / ms * 1e3, 1), "approx_TFLOPs": round(flops / ms / 1e9, 1),
                           "normals_rms_deg_vs_host_fp32": rms, "same_expert": "%d/%d" % (int(same.sum()), n_ref)}), flush=True)
 
+    # ---- the same kernels in bf16x3 mode (hi / lo pairs, [w_hi | w_hi | w_lo] weights: 3 x the tensor work, fp32-grade) ----
+    if os.environ.get("X3", "1") != "0":
+        mb._lib.set_option("pool_variant", 0)
+        mb._lib.set_option("conv_variant", 0)
+        tc3 = TensorCoreExperts(net, precision="bf16x3")
+        for bsz in sorted({B, int(os.environ.get("B_X3", 512))}):
+            qq = np.random.RandomState(1).choice(100000, bsz, replace=False)
+            x = mb.mups_features(index, gmm, qq, index.absolute_radii(RADIUS), 512, seed=SEED)
+            tc3.predict(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                tc3.predict(x)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            n_s, e_s, _ = tc3.predict(mups[:n_ref])
+            same = (e_s.cpu() == ref_e)
+            rms = float(angular_rms_deg(n_s.float().cpu()[same], ref_n[same])) if bool(same.any()) else None
+            print(json.dumps({"mode": "tcgen05 engine, bf16x3 (a_hi w_hi + a_lo w_hi + a_hi w_lo -> fp32 in TMEM)", "batch": bsz,
+                              "ms_per_batch": round(ms, 2), "queries_per_s": round(bsz / ms * 1e3, 1),
+                              "approx_TFLOPs_executed": round(3 * 6.0e10 * bsz / ms / 1e9, 1),
+                              "normals_rms_deg_vs_host_fp32": rms, "same_expert": "%d/%d" % (int(same.sum()), n_ref)}), flush=True)
+
 
 if __name__ == "__main__":
     main()

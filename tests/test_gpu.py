@@ -1196,6 +1196,97 @@ def test_tensor_core_consumer_three_scales():
     assert torch.isfinite(n_est).all() and rms < 1.0 and int(same.sum()) >= int(0.9 * len(q)) and float((prob - prob_ref).abs().max()) < 0.05
 
 
+def _triplet(t, off, w):
+    """(hi + lo as fp32, hi, lo, second hi) of the triplet at channels [off, off + 3 w) of a bf16 tensor."""
+    hi, lo, hi2 = t[..., off:off + w], t[..., off + w:off + 2 * w], t[..., off + 2 * w:off + 3 * w]
+    return hi.float() + lo.float(), hi, lo, hi2
+
+
+def test_bf16x3_split_and_pool_kernels():
+    """csrc/moe_split.cu: mups_split_bf16x3 (fp32 -> triplet [hi | lo | hi], hi = bf16(v), lo = bf16(v - hi): bit-exact, zero
+    padding of the tail, untouched neighbours) and mups_pool3d_bf16x3 (TF 'SAME' average / 2-2 max pool on hi + lo)."""
+    from nesti_net_b200 import moe_engine as me
+    from nesti_net_b200.experts_net import avg_pool_same, max_pool_same
+    torch.manual_seed(5)
+    rows = 3 * 8 * 8 * 8
+    for (n_src, src_off, w_src, w_dst) in [(80, 20, 20, 32), (64, 0, 64, 64), (48, 8, 40, 40), (35, 3, 17, 24)]:
+        src = torch.randn((rows, n_src), device="cuda") * torch.logspace(-6, 3, n_src, device="cuda")
+        dst = torch.full((3, 8, 8, 8, 3 * w_dst + 16), 7.0, device="cuda", dtype=torch.bfloat16)
+        me.split_x3(src, src_off, w_src, dst, 8, w_dst)
+        torch.cuda.synchronize()
+        v = torch.zeros((rows, w_dst), device="cuda")
+        v[:, :w_src] = src[:, src_off:src_off + w_src]
+        hi = v.to(torch.bfloat16)
+        lo = (v - hi.float()).to(torch.bfloat16)
+        d = dst.view(rows, -1)
+        _, g_hi, g_lo, g_hi2 = _triplet(d, 8, w_dst)
+        assert torch.equal(g_hi, hi) and torch.equal(g_lo, lo) and torch.equal(g_hi2, hi)
+        assert torch.all(d[:, :8] == 7.0) and torch.all(d[:, 8 + 3 * w_dst:] == 7.0), "wrote outside its triplet"
+        # 16 significant bits: the pair reproduces v to 2^-17 relative
+        assert ((hi.float() + lo.float() - v).abs() <= 2.0 ** -16 * v.abs()).all()
+    for (D, k, is_max) in [(8, 3, False), (8, 5, False), (8, 2, False), (4, 3, False), (4, 4, False), (2, 2, False), (8, 2, True), (4, 2, True), (2, 2, True)]:
+        B, w, ct = 3, 24, 3 * 24 + 3 * 40 + 8
+        x = torch.full((B, D, D, D, ct), 3.0, device="cuda", dtype=torch.bfloat16)
+        val = torch.randn((B * D ** 3, w), device="cuda")
+        me.split_x3(val, 0, w, x, 3 * 40, w)                      # the triplet under test sits behind another segment
+        Do = D // 2 if is_max else D
+        y = torch.full((B, Do, Do, Do, 3 * w + 16), 7.0, device="cuda", dtype=torch.bfloat16)
+        me.pool3d_x3(x, 3 * 40, w, k, is_max, y, 16)
+        torch.cuda.synchronize()
+        v5 = _triplet(x, 3 * 40, w)[0].permute(0, 4, 1, 2, 3)
+        ref = (max_pool_same(v5, 2, 2) if is_max else avg_pool_same(v5, k)).permute(0, 2, 3, 4, 1)
+        got, g_hi, g_lo, g_hi2 = _triplet(y, 16, w)
+        assert torch.equal(g_hi, g_hi2) and torch.all(y[..., :16] == 7.0)
+        if is_max:
+            assert torch.equal(got, ref)
+        else:
+            assert ((got - ref).abs() <= 3e-5 * ref.abs() + 1e-6).all()
+
+
+def test_tensor_core_consumer_bf16x3_against_fp32_network():
+    """moe_engine.TensorCoreExperts(precision="bf16x3"): every operand carried as two bf16 numbers, a_hi w_hi + a_lo w_hi +
+    a_hi w_lo accumulated in fp32 by the SAME tcgen05 kernels over a three times longer channel axis.  Against the fp32
+    PyTorch network (TF32 off) on GPU MuPS of a real cloud: same expert for every query, normals within 0.01 degrees (the
+    plain bf16 mode: 0.2), gate probabilities within 1e-4.  The four-scale and the three-scale configuration (padded
+    42-filter expert) are both run."""
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg
+    from nesti_net_b200.moe_engine import TensorCoreExperts
+    for radius, nq, seed in (([0.01, 0.03, 0.05, 0.07], 96, 1234), ([0.01, 0.03, 0.07], 40, 99)):
+        pts = orc.synthetic_cloud(30000, cloud_id=9, noise=0.001)
+        w, mu, sg = grid_gmm(8, 0.0156)
+        q = np.random.RandomState(8).choice(30000, nq, replace=False)
+        index = mb.PointIndex(pts, cell_frac=max(radius))
+        mups = mb.mups_features(index, mb.gmm_handle(w, mu, sg), q, index.absolute_radii(radius), 512, seed=SEED)
+        torch.manual_seed(seed)
+        net = ExpertsNormalEstimator(n_rads=len(radius), n_gaussians=512, n_experts=7).eval()
+        with torch.no_grad():
+            for m in net.modules():
+                if isinstance(m, (torch.nn.BatchNorm3d, torch.nn.BatchNorm1d)):
+                    m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.6, 1.5); m.weight.uniform_(0.7, 1.3); m.bias.normal_(0, 0.05)
+                if isinstance(m, (torch.nn.Conv3d, torch.nn.Linear)):
+                    m.bias.normal_(0, 0.02)
+        net = net.cuda()
+        tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                prob_ref, n_ref = net(mups)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        tc = TensorCoreExperts(net, precision="bf16x3")
+        prob, n_est = tc.forward(mups)
+        torch.cuda.synchronize()
+        assert tuple(prob.shape) == tuple(prob_ref.shape) and tuple(n_est.shape) == tuple(n_ref.shape)
+        assert torch.isfinite(prob).all() and torch.isfinite(n_est).all()
+        same = prob.argmax(0) == prob_ref.argmax(0)
+        rms = angular_rms_deg(n_est.reshape(-1, 3), n_ref.reshape(-1, 3))
+        dprob = float((prob - prob_ref).abs().max())
+        rel = float((n_est - n_ref).abs().max() / n_ref.abs().max())
+        print("bf16x3 consumer vs fp32 network (%d scales): angular RMS %.3g deg over all experts, max rel %.3g, same expert %d/%d, "
+              "max |dprob| %.3g" % (len(radius), rms, rel, int(same.sum()), len(q), dprob))
+        assert rms < 0.01 and bool(same.all()) and dprob < 1e-4
+
+
 def test_downstream_moe_normals():
     """Fourth gate of BASELINE.json: the same randomly initialised Mixture-of-Experts (PyTorch restatement of
     models/experts_n_est.py, fp32) evaluated on oracle MuPS and on GPU MuPS gives normals within 1e-4 angular

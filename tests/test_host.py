@@ -68,6 +68,13 @@ def test_argument_validation_without_compute():
     assert L.mups_avgpool3d_bn_relu(one, 4, 8, 64, 0, 64, 1, one, one, 1, one, 64, 0, None) == _lib.MUPS_ERR_INVALID
     assert b"identity" in L.mups_last_error()
     assert L.mups_pool3d(one, 4, 8, 64, 0, 64, 3, 1, one, None) == _lib.MUPS_ERR_INVALID        # max pool: window 2 only
+    assert L.mups_split_bf16x3(one, 10, 80, 20, 20, one, 96, 0, 30, None) == _lib.MUPS_ERR_INVALID  # part width: a multiple of 8
+    assert b"multiple of 8" in L.mups_last_error()
+    assert L.mups_split_bf16x3(one, 10, 80, 70, 20, one, 96, 0, 32, None) == _lib.MUPS_ERR_INVALID  # columns [70, 90) of 80
+    assert L.mups_split_bf16x3(one, 10, 80, 20, 20, one, 96, 8, 32, None) == _lib.MUPS_ERR_INVALID  # triplet [8, 104) of 96 channels
+    assert b"triplet" in L.mups_last_error()
+    assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 0, 32, 3, 1, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # max pool: window 2 only
+    assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 8, 32, 3, 0, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # triplet [8, 104) of 96
     for name, top in ((b"pool_variant", 1), (b"conv_variant", 8)):
         assert L.mups_set_option(name, top + 1) == _lib.MUPS_ERR_INVALID and L.mups_set_option(name, 0) == _lib.MUPS_OK
     if not torch.cuda.is_available():
@@ -370,3 +377,73 @@ def test_experts_net_against_reference_text_on_emulated_tf(golden_dir, case):
     ck = {"fc1noise/bn/fc1noise/bn/moments/Squeeze/ExponentialMovingAverage:0": 1,
           "fc1noise/bn/fc1noise/bn/moments/Squeeze_1/ExponentialMovingAverage": 2, "fc1noise/weights": 3}
     assert canonical_tf_names(ck) == {"fc1noise/bn/moving_mean": 1, "fc1noise/bn/moving_variance": 2, "fc1noise/weights": 3}
+
+
+def test_bf16x3_engine_logic_on_emulated_ops(monkeypatch):
+    """Host logic of the consumer's bf16x3 mode (moe_engine.TensorCoreExperts(precision="bf16x3")): segment / triplet
+    bookkeeping, the [w_hi | w_hi | w_lo] weight expansion, channel offsets of every split -- with the three device entry
+    points it is built from (mups_conv3d_bn_relu with fp32 output, mups_split_bf16x3, mups_pool3d_bf16x3) replaced by torch
+    emulations of their documented semantics.  The emulated forward must agree with the fp32 network to fp32-grade accuracy
+    (plain bf16 is three orders of magnitude away).  The real kernels are checked on the GPU (tests/test_gpu.py)."""
+    import torch.nn.functional as F
+    from nesti_net_b200 import moe_engine as me
+    from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg, avg_pool_same
+
+    def emu_conv(x, cin_off, cin, layer, out=None, cout_off=0, out_f32=None):
+        assert out is None and out_f32 is not None, "the bf16x3 mode only uses the convolution's fp32 output"
+        assert x.dtype == torch.bfloat16 and cin % 8 == 0 and cin_off % 8 == 0 and cin <= layer.cin_pad
+        xs = x.float()[..., cin_off:cin_off + cin]
+        if xs.ndim == 2:
+            xs = xs[:, None, None, None, :]
+        k = layer.k
+        w = layer.w.float()[:, :, :cin].reshape(k, k, k, layer.cout_pad, cin).permute(3, 4, 0, 1, 2)
+        pl, pr = (k - 1) // 2, k - 1 - (k - 1) // 2                       # TF 'SAME': the smaller half first
+        y = F.conv3d(F.pad(xs.permute(0, 4, 1, 2, 3), (pl, pr, pl, pr, pl, pr)), w)
+        y = y.permute(0, 2, 3, 4, 1).reshape(-1, layer.cout_pad) * layer.scale + layer.shift
+        out_f32.copy_(torch.relu(y) if layer.relu else y)
+        return out_f32
+
+    def put_triplet(dst2d, off, w, v):
+        hi = v.to(torch.bfloat16)
+        lo = (v - hi.float()).to(torch.bfloat16)
+        dst2d[:, off:off + w], dst2d[:, off + w:off + 2 * w], dst2d[:, off + 2 * w:off + 3 * w] = hi, lo, hi
+
+    def emu_split(src, src_off, w_src, dst, dst_off, w_dst):
+        assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and w_dst % 8 == 0 and dst_off % 8 == 0
+        assert dst_off + 3 * w_dst <= dst.shape[-1] and src_off + w_src <= src.shape[-1]
+        v = torch.zeros((src.shape[0], w_dst))
+        v[:, :w_src] = src[:, src_off:src_off + w_src]
+        put_triplet(dst.view(-1, dst.shape[-1]), dst_off, w_dst, v)
+
+    def emu_pool(x, c_off, w, k, is_max, y, y_off):
+        assert c_off % 8 == 0 and w % 8 == 0 and c_off + 3 * w <= x.shape[-1] and y_off + 3 * w <= y.shape[-1]
+        v = (x[..., c_off:c_off + w].float() + x[..., c_off + w:c_off + 2 * w].float()).permute(0, 4, 1, 2, 3)
+        assert torch.equal(x[..., c_off:c_off + w], x[..., c_off + 2 * w:c_off + 3 * w]), "third part of a triplet is hi again"
+        p = F.max_pool3d(v, 2, 2) if is_max else avg_pool_same(v, k)
+        put_triplet(y.view(-1, y.shape[-1]), y_off, w, p.permute(0, 2, 3, 4, 1).reshape(-1, w))
+
+    monkeypatch.setattr(me, "conv3d_bn_relu", emu_conv)
+    monkeypatch.setattr(me, "split_x3", emu_split)
+    monkeypatch.setattr(me, "pool3d_x3", emu_pool)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)      # the constructor refuses to run without a device
+
+    torch.manual_seed(7)
+    net = ExpertsNormalEstimator(n_rads=2, n_gaussians=512, n_experts=3).eval()     # experts on scale 0, scale 1, both scales
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, (torch.nn.BatchNorm3d, torch.nn.BatchNorm1d)):
+                m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.6, 1.5); m.weight.uniform_(0.7, 1.3); m.bias.normal_(0, 0.05)
+    mups = (torch.rand(2, 8, 8, 8, 40) - 0.5) * 0.2
+    with torch.no_grad():
+        prob_ref, n_ref = net(mups)
+    with pytest.raises(ValueError):
+        me.TensorCoreExperts(net, device="cpu", precision="fp8")
+    tc = me.TensorCoreExperts(net, device="cpu", precision="bf16x3")
+    assert tc.gate.out_segs is not None and tc.gate.steps[0].one.cin_pad == 3 * 64
+    prob, n_est = tc.forward(mups)
+    assert tuple(prob.shape) == tuple(prob_ref.shape) and tuple(n_est.shape) == tuple(n_ref.shape)
+    rms = angular_rms_deg(n_est.reshape(-1, 3), n_ref.reshape(-1, 3))
+    rel = float((n_est - n_ref).abs().max() / n_ref.abs().max())
+    dprob = float((prob - prob_ref).abs().max())
+    print("bf16x3 (emulated ops) vs fp32 network: angular RMS %.3g deg, max rel %.3g, max |dprob| %.3g" % (rms, rel, dprob))
+    assert rms < 5e-3 and rel < 1e-4 and dprob < 1e-5
