@@ -751,6 +751,30 @@ def run_clouds(args, cfg):
                                  "probabilities to pinned host memory; random-init 7-expert network; every rank its own cloud and consumer",
                           "cudnn_strict_fp32_queries_per_s": 774, "cudnn_source": "profiles/r02_moe.jsonl"}
         del tc, pipe_n, est
+        if "x3" not in skip:
+            # the same path with the consumer in bf16x3 mode (hi / lo bf16 pairs: a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32 on the
+            # same tcgen05 kernels): normals within ~1e-3 degrees of the fp32 network (tests/test_gpu.py) at 3 x the tensor work
+            torch.manual_seed(1234)
+            tc3 = TensorCoreExperts(ExpertsNormalEstimator(n_rads=S, n_gaussians=G, n_experts=7).eval().to(dev), precision="bf16x3")
+            est3 = CloudNormalEstimator(tc3, gmm, RADIUS, P, seed=SEED, chunk=1024)
+            nq3 = max(1024, nq_n // 2)
+            est3(hosts[0], qn_host[:1024])
+            torch.cuda.synchronize()
+            barrier()
+            w0 = time.perf_counter()
+            nrm3, exp3, _ = est3(hosts[(1 + rank) % len(hosts)], qn_host[:nq3])
+            nt3 = max_over_ranks(time.perf_counter() - w0, dev, world)
+            barrier()
+            same3 = exp3 == exp_host[:nq3]
+            cosang = np.clip(np.abs((nrm3[same3] * nrm_host[:nq3][same3]).sum(1)) /
+                             np.maximum(np.linalg.norm(nrm3[same3], axis=1) * np.linalg.norm(nrm_host[:nq3][same3], axis=1), 1e-30), 0.0, 1.0)
+            e2e["normals"]["bf16x3"] = {
+                "value": int(nrm3.shape[0]) * n_gpus / nt3, "unit": UNIT, "queries": int(nrm3.shape[0]) * n_gpus, "chunk_queries": est3.pipe.chunk,
+                "finite": bool(np.isfinite(nrm3).all()),
+                "bf16_vs_bf16x3_rms_deg": float(np.degrees(np.sqrt(np.mean(np.arccos(cosang) ** 2)))) if same3.any() else None,
+                "same_expert_as_bf16": "%d/%d" % (int(same3.sum()), int(nq3)),
+                "api": "the same call with moe_engine.TensorCoreExperts(precision='bf16x3') (csrc/moe_split.cu)"}
+            del tc3, est3
 
     cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                     "sample": "measured at N=1 only (see the N=1 line / --impl reference)"}
