@@ -30,7 +30,10 @@ def main():
     n_check = int(opts.get("CHECK", 32))
     P = int(opts.get("P", 512))
     for name in args:
-        if name == "C4":
+        if name == "C2":                      # configs[1]: the 100 k-point cloud of the default bench line
+            pts = synthetic_cloud(100000, cloud_id=0)
+            nq = min(nq, 100000)
+        elif name == "C4":
             pts = synthetic_cloud(2000000, cloud_id=1, kind="scan")
         else:
             pts = synthetic_cloud(10000000, cloud_id=2)
@@ -49,8 +52,10 @@ def main():
                     ("hier", 2, 0.0625, 2), ("hier", 2, 0.085, 2), ("flat", 1, 0.34, 2)]
         if opts.get("VARIANTS"):
             variants = [variants[int(i)] for i in opts["VARIANTS"].split(",")]
+        if opts.get("SPEC"):                  # SPEC=flat:1.0:1;hier:0.25:2 ... (kernel : cell scale : CTA order)
+            variants = [(k, 1 if k == "flat" else 2, float(sc), int(o)) for k, sc, o in (v.split(":") for v in opts["SPEC"].split(";"))]
         for kname, kernel, scale, order in variants:
-            nq_v = nq if kname == "hier" else min(nq, 8192)
+            nq_v = nq if (kname == "hier" or name == "C2") else min(nq, 8192)
             _lib.set_option("query_kernel", kernel)
             _lib.set_option("query_order", order)
             torch.cuda.synchronize()
