@@ -409,22 +409,24 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 // slices = two 128-voxel tiles, plus the halo; out-of-volume slices / rows / columns zero-filled by the TMA unit) and issues
 // the MMAs of all k dz-taps of both tiles from it, the descriptor start advanced by (2 u + dz) * 8 KB.  Activation traffic per
 // tap falls from 32 KB to (4 + k - 1) * 8 / k KB (12.8 KB at k = 5); the weights stream through their own ring.
-struct HaloArgs { int na, nb, a_box_bytes, swap, ext, nz; };   // A stages, B stages, bytes of one activation box, operand roles swapped,
-                                                                 // z-slices per box, output z-slices per CTA (4, or 8 = the whole sample)
+struct HaloArgs { int na, nb, a_box_bytes, swap, ext, nz, pair; };   // A stages, B stages, bytes of one activation box, operand roles swapped,
+                                                                 // z-slices per box, output z-slices per CTA (4, or 8 = the whole sample),
+                                                                 // CTA pair sharing every weight tile by TMA multicast (cluster of 2)
 
 // Epilogue of the z-halo kernel with SWAPPED operand roles (accumulator = [128 output channels (TMEM lanes)] x [256 voxels
 // (columns)]): a thread owns one output channel, a warp's store covers 32 consecutive channels of one voxel (64 bytes).
 __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_t bar_acc, uint32_t tmem_base, int warp, int lane, int n0,
-                                                      long long voxel0, int voxels) {
+                                                      long long voxel0, int voxels, bool live) {
     mbar_wait(bar_acc, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quarter = warp & 3;
     const int co = n0 + quarter * 32 + lane;
     const bool real = co < a.Cout;
     const float sc = real ? __ldg(a.scale + co) : 0.f, sh = real ? __ldg(a.shift + co) : 0.f;
-    __nv_bfloat16* ycol = a.y ? a.y + voxel0 * a.y_stride + a.cout_off + co : nullptr;
-    float* fcol = a.y_f32 ? a.y_f32 + voxel0 * (long long)a.Cout + co : nullptr;
-    for (int j0 = 0; j0 < voxels; j0 += 64) {           // voxels is 256 or 512: four TMEM loads in flight per wait
+    // live == false: the all-out-of-bounds partner of an odd batch's last CTA pair -- it waits for its MMAs, stores nothing
+    __nv_bfloat16* ycol = (a.y && live) ? a.y + voxel0 * a.y_stride + a.cout_off + co : nullptr;
+    float* fcol = (a.y_f32 && live) ? a.y_f32 + voxel0 * (long long)a.Cout + co : nullptr;
+    for (int j0 = 0; j0 < (live ? voxels : 0); j0 += 64) {           // voxels is 256 or 512: four TMEM loads in flight per wait
         uint32_t v[4][16];
 #pragma unroll
         for (int h = 0; h < 4; ++h) tmem_ld16_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j0 + 16 * h), v[h]);
@@ -444,7 +446,8 @@ __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_
 }
 
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvArgs a, const HaloArgs h) {
+conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_half,
+                    const ConvArgs a, const HaloArgs h) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = a.n_tile * kTileK * 2;
@@ -462,7 +465,8 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-        for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+        // pair mode: a weight stage may be refilled once BOTH CTAs' MMAs have read it (each CTA writes half of it into both)
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, h.pair ? 2 : 1); }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -472,8 +476,10 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (h.pair) cluster_sync_all();     // the peer's barriers exist before anything is multicast into this CTA
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = h.pair ? cluster_ctarank() : 0u;
 
     // this CTA: sample blockIdx.x / 2, z-slices [4 (blockIdx.x & 1), +4) = tiles 2 blockIdx.x, 2 blockIdx.x + 1; n_tile channels at n0
     const int n0 = blockIdx.y * a.n_tile;
@@ -504,6 +510,10 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 for (int i = 0, dz = a.pl; i < a.k; ++i, dz = dz + 1 == a.k ? 0 : dz + 1) {    // dz = pl first (see the MMA loop)
                     mbar_wait(bar_bempty + 8 * sb, pb);
                     mbar_expect_tx(bar_bfull + 8 * sb, (uint32_t)b_bytes);
+                    if (h.pair)         // this CTA fetches its half of the tile's rows; the TMA unit writes it into both shared memories
+                        tma_load_3d_multicast(smem_u32(smem_b + (size_t)sb * b_bytes) + crank * (uint32_t)(b_bytes >> 1), &map_w_half, bar_bfull + 8 * sb,
+                                              kb * kTileK, n0 + (int)crank * (a.n_tile >> 1), (dz * a.k + dy) * a.k + dx, (uint16_t)3);
+                    else
                     tma_load_3d(smem_u32(smem_b + (size_t)sb * b_bytes), &map_w, bar_bfull + 8 * sb, kb * kTileK, n0, (dz * a.k + dy) * a.k + dx);
                     if (++sb == h.nb) { sb = 0; pb ^= 1; }
                 }
@@ -547,7 +557,8 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         for (int k = 0; k < kTileK / 16; ++k)
                             umma_bf16(tmem_base + (uint32_t)(u * a.n_tile), da + 2 * k, db + 2 * k, idesc, (st > 0 || i > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(bar_bempty + 8 * sb);
+                    if (h.pair) umma_commit_multicast(bar_bempty + 8 * sb, (uint16_t)3);   // frees the stage in both CTAs
+                    else umma_commit(bar_bempty + 8 * sb);
                     if (i == a.k - 1) {
                         umma_commit(bar_aempty + 8 * sa);    // the box is free once the MMAs of its last tap have read it
                         if (st == steps - 1) umma_commit(bar_acc);
@@ -559,11 +570,12 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             if (++sa == h.na) { sa = 0; pa ^= 1; }
         }
     } else if (h.swap) {
-        conv_epilogue_swapped(a, bar_acc, tmem_base, warp, lane, n0, (long long)tb0[0] * 512 + tz0[0] * 64, h.nz * 64);
+        conv_epilogue_swapped(a, bar_acc, tmem_base, warp, lane, n0, (long long)tb0[0] * 512 + tz0[0] * 64, h.nz * 64, sample < a.B);
     } else {
         conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
     }
     __syncthreads();
+    if (h.pair) cluster_sync_all();     // nobody leaves while the peer may still write into this CTA's shared memory / barriers
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -957,7 +969,7 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
 
     // z-halo kernel: 8^3 volumes, k > 1, both accumulators in TMEM (conv_variant 2 forces the per-tap kernel)
     const bool zhalo = D == 8 && k >= 2 && n_tile <= 128 && g_conv_variant.load() != 2;
-    HaloArgs h{0, 0, 0, 0, 0, 4};
+    HaloArgs h{0, 0, 0, 0, 0, 4, 0};
     if (zhalo) {
         a.m_sub = 2;
         h.swap = (n_tile == 128 && g_conv_variant.load() != 3) ? 1 : 0;     // conv_variant 3: z-halo without the operand swap
@@ -1000,8 +1012,38 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     }
     if (zhalo) {
         MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_zhalo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv3d_zhalo_kernel<<<dim3((unsigned)(h.nz == 8 ? m_tiles / 4 : m_tiles / 2), (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-            map_x, map_w, a, h);
+        unsigned gx = (unsigned)(h.nz == 8 ? m_tiles / 4 : m_tiles / 2);
+        // conv_variant 9: CTA pairs (clusters of two CTAs: two samples, or the two halves of one) that share every weight tile -- each
+        // CTA fetches half of its rows and the TMA unit multicasts them into both shared memories: a fifth to a quarter less L2 -> SM
+        // traffic per CTA (the weights are 3 x 16 of 112 KB per activation box at k = 3, 5 x 16 of 144 KB at k = 5)
+        h.pair = (g_conv_variant.load() == 9 && gx >= 2 * kNumSMs) ? 1 : 0;
+        if (!h.pair) {
+            conv3d_zhalo_kernel<<<dim3(gx, (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, map_w, a, h);
+            MUPS_CHECK_LAUNCH();
+            return MUPS_OK;
+        }
+        CUtensorMap map_wh;
+        {
+            const cuuint64_t dims[3] = {(cuuint64_t)cin_w, (cuuint64_t)cout, (cuuint64_t)(k * k * k)};
+            const cuuint64_t strides[2] = {(cuuint64_t)cin_w * 2, (cuuint64_t)cin_w * 2 * cout};
+            const cuuint32_t box[3] = {(cuuint32_t)kTileK, (cuuint32_t)(n_tile / 2), 1};
+            const cuuint32_t es[3] = {1, 1, 1};
+            const CUresult r = enc(&map_wh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_bf16_dev), dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("mups_conv3d_bn_relu: half weight tensor map rejected (CUresult %d)", (int)r); return MUPS_ERR_CUDA; }
+        }
+        gx = (gx + 1) & ~1u;                                 // an odd batch's last CTA gets an all-out-of-bounds partner
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, (unsigned)(cout / n_tile));
+        cfg.blockDim = dim3(kConvThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = static_cast<cudaStream_t>(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        MUPS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3d_zhalo_kernel, map_x, map_w, map_wh, a, h));
         MUPS_CHECK_LAUNCH();
         return MUPS_OK;
     }

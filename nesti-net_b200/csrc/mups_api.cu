@@ -114,7 +114,7 @@ int mups_set_option(const char* name, int64_t value) {
         return MUPS_OK;
     }
     if (!strcmp(name, "pool_variant") || !strcmp(name, "conv_variant")) {
-        MUPS_REQUIRE(value >= 0 && value <= (name[0] == 'p' ? 1 : 8), "mups_set_option: %s=%lld out of range", name, (long long)value);
+        MUPS_REQUIRE(value >= 0 && value <= (name[0] == 'p' ? 1 : 9), "mups_set_option: %s=%lld out of range", name, (long long)value);
         (name[0] == 'p' ? g_pool_variant : g_conv_variant).store((int)value);
         return MUPS_OK;
     }

@@ -956,7 +956,8 @@ def _conv_reference(x, cin_off, cin, w, scale, shift, relu, k):
     (8, 2, 64, 0, 64, 32, 3), (8, 4, 128, 64, 64, 48, 2), (8, 5, 384, 0, 384, 256, 2), (8, 1, 384, 0, 384, 256, 40),
     (8, 3, 256, 0, 256, 128, 3), (8, 5, 136, 8, 128, 128, 2),
     (8, 3, 128, 0, 128, 128, 600), (8, 4, 64, 0, 64, 128, 593),
-    (8, 1, 128, 0, 128, 128, 160), (8, 1, 72, 8, 64, 512, 149), (4, 1, 256, 0, 256, 256, 1301)])
+    (8, 1, 128, 0, 128, 128, 160), (8, 1, 72, 8, 64, 512, 149), (4, 1, 256, 0, 256, 256, 1301),
+    (8, 3, 64, 0, 64, 128, 150), (8, 3, 96, 0, 96, 64, 151), (8, 5, 136, 8, 128, 128, 149)])
 def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     """mups_conv3d_bn_relu (tcgen05 / TMEM / TMA implicit GEMM, csrc/moe_conv.cu) against torch conv3d in fp32 on the same
     bf16-rounded operands: every volume edge and kernel edge of the reference's networks, 'SAME' padding for even kernels,
@@ -993,6 +994,19 @@ def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
         finally:
             _lib.set_option("conv_variant", 0)
         assert torch.equal(f32b, f32) and torch.equal(outb, out)
+    if D == 8 and k > 1 and cout <= 128 and B >= 148:
+        # conv_variant 9: the z-halo kernel as CTA pairs (clusters of two) that share every weight tile through TMA multicast --
+        # whole-sample CTAs of two samples (an odd batch gets an all-out-of-bounds partner), or the two halves of one sample;
+        # same MMAs in the same order
+        _lib.set_option("conv_variant", 9)
+        try:
+            f32p = torch.empty_like(f32)
+            outp = torch.full_like(out, 7.0)
+            me.conv3d_bn_relu(x, cin_off, cin, layer, outp, 8, f32p)
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_option("conv_variant", 0)
+        assert torch.equal(f32p, f32) and torch.equal(outp, out)
     if D == 8 and k > 1 and cout <= 128:
         # the default above was the z-halo kernel (one activation box per (dy, dx, channel block) serves all dz taps);
         # conv_variant 2 forces the per-tap kernel: same products, another summation order

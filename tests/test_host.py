@@ -75,7 +75,7 @@ def test_argument_validation_without_compute():
     assert b"triplet" in L.mups_last_error()
     assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 0, 32, 3, 1, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # max pool: window 2 only
     assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 8, 32, 3, 0, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # triplet [8, 104) of 96
-    for name, top in ((b"pool_variant", 1), (b"conv_variant", 8)):
+    for name, top in ((b"pool_variant", 1), (b"conv_variant", 9)):
         assert L.mups_set_option(name, top + 1) == _lib.MUPS_ERR_INVALID and L.mups_set_option(name, 0) == _lib.MUPS_OK
     if not torch.cuda.is_available():
         # no CPU fallback: a valid request fails loudly with MUPS_ERR_CUDA
