@@ -72,7 +72,8 @@ class CloudNormalEstimator(object):
     ``estimate_normals`` (same shared seeded selection, same features, same network), at the speed of the device path:
     what ``bench.py`` reports as ``e2e.normals``.
 
-    model: ``moe_engine.TensorCoreExperts`` (the tensor-core engine) or a CUDA ``ExpertsNormalEstimator``."""
+    model: ``moe_engine.TensorCoreExperts`` (the tensor-core engine; ``precision="bf16x3"`` for fp32-grade normals at a third of
+    the throughput) or a CUDA ``ExpertsNormalEstimator``."""
 
     def __init__(self, model, gmm, patch_radius, points_per_patch=512, seed=3627473, chunk=2048):
         self.model = model
