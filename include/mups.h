@@ -216,6 +216,12 @@ int mups_split_bf16x3(const float* src_dev, int64_t rows, int src_stride, int sr
  * reduced on hi + lo in fp32. */
 int mups_pool3d_bf16x3(const void* x_bf16_dev, int64_t B, int D, int c_total, int c_off, int w, int k, int is_max, void* y_bf16_dev,
                        int y_total, int y_off, mups_stream stream);
+/* The pool branch of an inception module in bf16x3 mode (models/experts_n_est.py:291-310): its 1^3 convolution has run first
+ * (raw fp32 output x_f32_dev [B, D, D, D, c], no bias -- it commutes with the pool); this is tf_util.avg_pool3d (window k >= 2,
+ * stride 1, 'SAME', mean over the valid cells) on that tensor followed by act(scale[ch] * pooled + shift[ch]) (the folded bias +
+ * batch norm + ReLU) written as the triplet at channels [y_off, y_off + 3 c) of y_bf16_dev [B, D, D, D, y_total]. */
+int mups_avgpool3d_f32_bn_relu_x3(const float* x_f32_dev, int64_t B, int D, int c, int k, const float* scale_dev, const float* shift_dev,
+                                  int relu, void* y_bf16_dev, int y_total, int y_off, mups_stream stream);
 
 #ifdef __cplusplus
 }

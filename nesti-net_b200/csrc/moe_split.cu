@@ -17,7 +17,13 @@
 //   pool3_x3_kernel    tf_util.avg_pool3d ('SAME', stride 1, mean over the valid cells; utils/tf_util.py:432-455) and
 //                      max_pool3d (2, stride 2; :406-430) from a triplet to a triplet: the window is reduced on
 //                      hi + lo in fp32 and split again
-// Both are memory-bound elementwise kernels (16-byte loads / stores, one thread per 8 channels).
+//   avgpool8_f32_x3_kernel / avgpool_f32_x3_kernel   the inception module's pool branch: its 1^3 convolution commutes with the
+//                      average pool (both linear), so the convolution runs first (raw fp32 output, n_filters instead of C_in
+//                      channels) and this kernel pools the fp32 tensor, applies the folded bias + batch norm + ReLU and writes
+//                      the triplet -- 8^3 volumes as a separable box sum on a shared-memory tile (every byte read once)
+// All are memory-bound kernels (16-byte loads / stores).
+#include <mutex>
+
 #include <cuda_bf16.h>
 
 #include "mups_common.cuh"
@@ -124,6 +130,128 @@ __global__ void __launch_bounds__(256) pool3_x3_kernel(const __nv_bfloat16* __re
     }
 }
 
+// fp32 [B, 8, 8, 8, c] -> TF 'SAME' average pool (window K, mean over the valid cells) -> act(scale * . + shift) -> triplet.
+// One CTA = one sample x 32 channels: the 512 x 32 tile is staged once in shared memory (64 KB) and the box sum is done
+// separably in place (three passes of 64 lines of 8 voxels, one warp per line, lane = channel).
+template <int K>
+__global__ void __launch_bounds__(256) avgpool8_f32_x3_kernel(const float* __restrict__ x, int c, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int relu, __nv_bfloat16* __restrict__ y,
+                                                              int y_total, int y_off) {
+    extern __shared__ __align__(16) float tile[];                  // [512 voxels][32 channels]
+    constexpr int D = 8, PL = (K - 1) / 2;
+    const int chunks = c >> 5;
+    const long long b = blockIdx.x / chunks;
+    const int chunk = blockIdx.x % chunks;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* src = x + b * 512 * (long long)c + chunk * 32;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {                         // 4096 float4 per tile: two batches of eight loads in flight
+        float4 raw[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = tid + (half * 8 + r) * 256;
+            raw[r] = __ldg(reinterpret_cast<const float4*>(src + (i >> 3) * (long long)c) + (i & 7));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = tid + (half * 8 + r) * 256;
+            *reinterpret_cast<float4*>(tile + (i >> 3) * 32 + (i & 7) * 4) = raw[r];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const int step = pass == 0 ? 1 : pass == 1 ? 8 : 64;
+        for (int l = warp; l < 64; l += 8) {
+            const int base = pass == 0 ? l * 8 : pass == 1 ? (l >> 3) * 64 + (l & 7) : l;
+            float r[D], o[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) r[i] = tile[(base + i * step) * 32 + lane];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                float acc = 0.f;
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    const int j = i + d - PL;
+                    if (j >= 0 && j < D) acc += r[j];
+                }
+                o[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) tile[(base + i * step) * 32 + lane] = o[i];
+        }
+        __syncthreads();
+    }
+    __nv_bfloat16* dst = y + b * 512 * (long long)y_total + y_off + chunk * 32;
+    for (int i = tid; i < 512 * 4; i += 256) {
+        const int v = i >> 2, part = i & 3;
+        const int vx = v & 7, vy = (v >> 3) & 7, vz = v >> 6;
+        auto valid = [](int q) { return min(q - PL + K - 1, D - 1) - max(q - PL, 0) + 1; };
+        const float inv = 1.f / (float)(valid(vx) * valid(vy) * valid(vz));
+        const float4* sp = reinterpret_cast<const float4*>(tile + v * 32 + part * 8);
+        const float4 a0 = sp[0], a1 = sp[1];
+        float f[8] = {a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv, a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv};
+        const int c0 = chunk * 32 + part * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(f[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+            f[j] = relu ? fmaxf(t, 0.f) : t;
+        }
+        store_triplet(dst + v * (long long)y_total + part * 8, c, f);
+    }
+}
+
+// the same for the 4^3 / 2^3 volumes (and channel counts that are not multiples of 32): one thread per (voxel, 8 channels)
+__global__ void __launch_bounds__(256) avgpool_f32_x3_kernel(const float* __restrict__ x, long long B, int D, int c, int k,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                                             __nv_bfloat16* __restrict__ y, int y_total, int y_off) {
+    const int chunks = c >> 3;
+    const long long n = B * D * D * D * chunks;
+    const int pl = (k - 1) / 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long long v = i / chunks;
+        const int xo = (int)(v % D), yo = (int)((v / D) % D), zo = (int)((v / ((long long)D * D)) % D);
+        const long long b = v / ((long long)D * D * D);
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int cnt = 0;
+        for (int dz = 0; dz < k; ++dz) {
+            const int z = zo - pl + dz;
+            if (z < 0 || z >= D) continue;
+            for (int dy = 0; dy < k; ++dy) {
+                const int yy = yo - pl + dy;
+                if (yy < 0 || yy >= D) continue;
+                for (int dx = 0; dx < k; ++dx) {
+                    const int xx = xo - pl + dx;
+                    if (xx < 0 || xx >= D) continue;
+                    const float4* p = reinterpret_cast<const float4*>(x + (((b * D + z) * D + yy) * D + xx) * (long long)c + ch * 8);
+                    const float4 a0 = __ldg(p), a1 = __ldg(p + 1);
+                    acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                    acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+                    ++cnt;
+                }
+            }
+        }
+        const float inv = 1.f / (float)cnt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(acc[j] * inv, __ldg(scale + ch * 8 + j), __ldg(shift + ch * 8 + j));
+            acc[j] = relu ? fmaxf(t, 0.f) : t;
+        }
+        store_triplet(y + v * (long long)y_total + y_off + ch * 8, c, acc);
+    }
+}
+
+template <int K>
+static cudaError_t launch_avgpool8_f32_x3(const float* x, long long B, int c, const float* scale, const float* shift, int relu,
+                                          __nv_bfloat16* y, int y_total, int y_off, cudaStream_t st) {
+    constexpr int smem = 512 * 32 * 4;
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(avgpool8_f32_x3_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    avgpool8_f32_x3_kernel<K><<<(unsigned)(B * (c >> 5)), 256, smem, st>>>(x, c, scale, shift, relu, y, y_total, y_off);
+    return cudaGetLastError();
+}
+
 }  // namespace mups
 
 using namespace mups;
@@ -162,6 +290,34 @@ int mups_pool3d_bf16x3(const void* x_bf16_dev, int64_t B, int D, int c_total, in
     const int grid = (int)((n + 255) / 256 < 32 * kNumSMs ? (n + 255) / 256 : 32 * kNumSMs);
     pool3_x3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16_dev), B, D, c_total, c_off, w, k,
                                                                            is_max, static_cast<__nv_bfloat16*>(y_bf16_dev), y_total, y_off);
+    MUPS_CHECK_LAUNCH();
+    return MUPS_OK;
+}
+
+int mups_avgpool3d_f32_bn_relu_x3(const float* x_f32_dev, int64_t B, int D, int c, int k, const float* scale_dev, const float* shift_dev,
+                                  int relu, void* y_bf16_dev, int y_total, int y_off, mups_stream stream) {
+    MUPS_REQUIRE(x_f32_dev && y_bf16_dev && scale_dev && shift_dev, "mups_avgpool3d_f32_bn_relu_x3: NULL buffer");
+    MUPS_REQUIRE(B >= 1 && B < (1ll << 30) && (D == 2 || D == 4 || D == 8), "mups_avgpool3d_f32_bn_relu_x3: B=%lld, volume edge %d", (long long)B, D);
+    MUPS_REQUIRE(c >= 8 && c % 8 == 0, "mups_avgpool3d_f32_bn_relu_x3: channels %d must be a multiple of 8", c);
+    MUPS_REQUIRE(k >= 2 && k <= 5, "mups_avgpool3d_f32_bn_relu_x3: window %d", k);
+    MUPS_REQUIRE(y_total % 8 == 0 && y_off >= 0 && y_off % 8 == 0 && y_off + 3 * c <= y_total,
+                 "mups_avgpool3d_f32_bn_relu_x3: output triplet (3 x %d of %d at %d)", c, y_total, y_off);
+    MUPS_REQUIRE((reinterpret_cast<uintptr_t>(x_f32_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16_dev) & 15) == 0,
+                 "mups_avgpool3d_f32_bn_relu_x3: buffers must be 16-byte aligned");
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* y = static_cast<__nv_bfloat16*>(y_bf16_dev);
+    if (D == 8 && c % 32 == 0 && (long long)B * (c >> 5) <= 0x7FFFFFFFll) {
+        const cudaError_t e = k == 2 ? launch_avgpool8_f32_x3<2>(x_f32_dev, B, c, scale_dev, shift_dev, relu, y, y_total, y_off, st)
+                            : k == 3 ? launch_avgpool8_f32_x3<3>(x_f32_dev, B, c, scale_dev, shift_dev, relu, y, y_total, y_off, st)
+                            : k == 4 ? launch_avgpool8_f32_x3<4>(x_f32_dev, B, c, scale_dev, shift_dev, relu, y, y_total, y_off, st)
+                                     : launch_avgpool8_f32_x3<5>(x_f32_dev, B, c, scale_dev, shift_dev, relu, y, y_total, y_off, st);
+        if (e != cudaSuccess) { set_error("mups_avgpool3d_f32_bn_relu_x3: %s", cudaGetErrorString(e)); return MUPS_ERR_CUDA; }
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return MUPS_OK;
+    }
+    const long long n = (long long)B * D * D * D * (c / 8);
+    const int grid = (int)((n + 255) / 256 < 32 * kNumSMs ? (n + 255) / 256 : 32 * kNumSMs);
+    avgpool_f32_x3_kernel<<<grid, 256, 0, st>>>(x_f32_dev, B, D, c, k, scale_dev, shift_dev, relu, y, y_total, y_off);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;
 }

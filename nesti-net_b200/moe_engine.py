@@ -160,6 +160,16 @@ def pool3d_x3(x, c_off, w, k, is_max, y, y_off):
                                                   ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "mups_pool3d_bf16x3")
 
 
+def avgpool_f32_x3(src, B, D, c, k, scale, shift, relu, out, y_off):
+    """fp32 src [B * D^3, c] (a convolution's raw output) -> TF 'SAME' average pool (window k) -> act(scale * . + shift) -> the
+    triplet at channels [y_off, y_off + 3 c) of out (mups_avgpool3d_f32_bn_relu_x3)."""
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().mups_avgpool3d_f32_bn_relu_x3(_ptr(src), int(B), int(D), int(c), int(k), _ptr(scale), _ptr(shift),
+                                                             1 if relu else 0, _ptr(out), int(out.shape[-1]), int(y_off),
+                                                             ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream)),
+                   "mups_avgpool3d_f32_bn_relu_x3")
+
+
 def _pool_segments_x3(x, c_off, segs, k, is_max):
     """Pool the logical channels [c_off, c_off + sum(segs)) of a triplet tensor segment by segment -> a new triplet tensor with
     the same segments."""
@@ -266,6 +276,15 @@ class _PackedInceptionX3(object):
         self.nf = self.one.cout_pad
         self.a, self.b = mk(m.a, None, self.nf, [self.nf]), mk(m.b, None, self.nf, [self.nf])
         self.ab = _fuse_branches(self.a, self.b) if (self.a.cout_pad + self.b.cout_pad <= 128 and self.a.k < self.b.k) else None
+        if self.k0 > 1:
+            # the pool branch's 1^3 convolution commutes with the average pool: it runs FIRST, raw (no bias, no batch norm, no
+            # ReLU), on n_filters instead of C_in channels; the pool applies the folded bias + batch norm + ReLU (as in the bf16 mode)
+            raw = PackedConv.__new__(PackedConv)
+            raw.__dict__.update(self.pool.__dict__)
+            raw.relu = False
+            raw.scale, raw.shift = torch.zeros_like(self.pool.scale), torch.zeros_like(self.pool.shift)
+            raw.scale[:self.pool.cout] = 1.0
+            self.pool_raw = raw
         self.c_out = 2 * self.nf + self.a.cout_pad + self.b.cout_pad
         self.out_segs = [self.nf, self.a.cout_pad, self.b.cout_pad, self.nf]
         real = lambda l, off: [off + i for i in range(l.cout)]
@@ -285,10 +304,10 @@ class _PackedInceptionX3(object):
             split_x3(conv3d_f32(out, 0, 3 * nf, self.a), 0, ap, out, 3 * nf, ap)
             split_x3(conv3d_f32(out, 0, 3 * nf, self.b), 0, bp, out, 3 * (nf + ap), bp)
         if self.k0 == 1:                         # a 1-wide average pool is the identity
-            t = conv3d_f32(x, 3 * cin_off, 3 * cin, self.pool)
+            split_x3(conv3d_f32(x, 3 * cin_off, 3 * cin, self.pool), 0, nf, out, 3 * (nf + ap + bp), nf)
         else:
-            t = conv3d_f32(_pool_segments_x3(x, cin_off, self.in_segs, self.k0, False), 0, 3 * cin, self.pool)
-        split_x3(t, 0, nf, out, 3 * (nf + ap + bp), nf)
+            t = conv3d_f32(x, 3 * cin_off, 3 * cin, self.pool_raw)
+            avgpool_f32_x3(t, x.shape[0], x.shape[1], nf, self.k0, self.pool.scale, self.pool.shift, True, out, 3 * (nf + ap + bp))
         return out
 
 

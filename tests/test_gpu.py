@@ -1255,6 +1255,20 @@ def test_bf16x3_split_and_pool_kernels():
             assert torch.equal(got, ref)
         else:
             assert ((got - ref).abs() <= 3e-5 * ref.abs() + 1e-6).all()
+    # the pool branch of an inception module: raw fp32 convolution output -> average pool -> scale / shift / ReLU -> triplet
+    for (D, k, c, relu) in [(8, 3, 64, True), (8, 5, 32, True), (8, 2, 96, False), (8, 4, 128, True), (8, 3, 40, True), (4, 2, 48, True),
+                            (4, 3, 64, False), (2, 2, 64, True)]:
+        B = 3
+        src = torch.randn((B * D ** 3, c), device="cuda")
+        scale, shift = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.3
+        y = torch.full((B, D, D, D, 3 * c + 24), 7.0, device="cuda", dtype=torch.bfloat16)
+        me.avgpool_f32_x3(src, B, D, c, k, scale, shift, relu, y, 8)
+        torch.cuda.synchronize()
+        ref = avg_pool_same(src.view(B, D, D, D, c).permute(0, 4, 1, 2, 3), k).permute(0, 2, 3, 4, 1) * scale + shift
+        ref = torch.relu(ref) if relu else ref
+        got, g_hi, g_lo, g_hi2 = _triplet(y, 8, c)
+        assert torch.equal(g_hi, g_hi2) and torch.all(y[..., :8] == 7.0) and torch.all(y[..., 8 + 3 * c:] == 7.0)
+        assert ((got - ref).abs() <= 3e-5 * ref.abs() + 2e-6).all(), (D, k, c)
 
 
 def test_tensor_core_consumer_bf16x3_against_fp32_network():

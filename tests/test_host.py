@@ -75,6 +75,8 @@ def test_argument_validation_without_compute():
     assert b"triplet" in L.mups_last_error()
     assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 0, 32, 3, 1, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # max pool: window 2 only
     assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 8, 32, 3, 0, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # triplet [8, 104) of 96
+    assert L.mups_avgpool3d_f32_bn_relu_x3(one, 4, 8, 64, 1, one, one, 1, one, 192, 0, None) == _lib.MUPS_ERR_INVALID  # window >= 2
+    assert L.mups_avgpool3d_f32_bn_relu_x3(one, 4, 8, 64, 3, one, one, 1, one, 192, 8, None) == _lib.MUPS_ERR_INVALID  # triplet [8, 200) of 192
     for name, top in ((b"pool_variant", 1), (b"conv_variant", 9)):
         assert L.mups_set_option(name, top + 1) == _lib.MUPS_ERR_INVALID and L.mups_set_option(name, 0) == _lib.MUPS_OK
     if not torch.cuda.is_available():
@@ -422,6 +424,12 @@ def test_bf16x3_engine_logic_on_emulated_ops(monkeypatch):
         p = F.max_pool3d(v, 2, 2) if is_max else avg_pool_same(v, k)
         put_triplet(y.view(-1, y.shape[-1]), y_off, w, p.permute(0, 2, 3, 4, 1).reshape(-1, w))
 
+    def emu_avgpool_f32(src, B, D, c, k, scale, shift, relu, out, y_off):
+        assert src.dtype == torch.float32 and tuple(src.shape) == (B * D ** 3, c) and k >= 2 and y_off + 3 * c <= out.shape[-1]
+        p = avg_pool_same(src.view(B, D, D, D, c).permute(0, 4, 1, 2, 3), k).permute(0, 2, 3, 4, 1).reshape(-1, c) * scale + shift
+        put_triplet(out.view(-1, out.shape[-1]), y_off, c, torch.relu(p) if relu else p)
+
+    monkeypatch.setattr(me, "avgpool_f32_x3", emu_avgpool_f32)
     monkeypatch.setattr(me, "conv3d_bn_relu", emu_conv)
     monkeypatch.setattr(me, "split_x3", emu_split)
     monkeypatch.setattr(me, "pool3d_x3", emu_pool)
