@@ -130,6 +130,38 @@ __global__ void __launch_bounds__(256) pool3_x3_kernel(const __nv_bfloat16* __re
     }
 }
 
+// tf.nn.max_pool3d(2, stride 2) from a triplet to a triplet (D even): one thread per (output voxel, 8-channel chunk), the sixteen
+// 16-byte loads of its window (hi and lo of eight cells) issued back to back, 32-bit index arithmetic.  The maximum of hi + lo
+// is one of the window's values, so the output pair is exact.
+__global__ void __launch_bounds__(256) maxpool2_x3_kernel(const __nv_bfloat16* __restrict__ x, unsigned n, int D, int ct, int x_off, int w,
+                                                          __nv_bfloat16* __restrict__ y, int y_ct, int y_off) {
+    const unsigned chunks = (unsigned)w >> 3, Do = (unsigned)D >> 1;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned ch = i % chunks, v = i / chunks;
+        const unsigned xo = v % Do, yo = (v / Do) % Do, zo = (v / (Do * Do)) % Do, b = v / (Do * Do * Do);
+        const size_t vin = (((size_t)b * D + 2 * zo) * D + 2 * yo) * D + 2 * xo;
+        const uint4* p = reinterpret_cast<const uint4*>(x + vin * ct + x_off) + ch;
+        const size_t sx = (size_t)ct / 8, sy = sx * D, sz = sy * D, sl = (size_t)w / 8;      // strides in 16-byte units
+        uint4 hi[8], lo[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const uint4* q = p + (t & 1) * sx + ((t >> 1) & 1) * sy + (t >> 2) * sz;
+            hi[t] = __ldg(q);
+            lo[t] = __ldg(q + sl);
+        }
+        float m[8];
+        join8(hi[0], lo[0], m);
+#pragma unroll
+        for (int t = 1; t < 8; ++t) {
+            float f[8];
+            join8(hi[t], lo[t], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+        }
+        store_triplet(y + (size_t)v * y_ct + y_off + ch * 8, w, m);
+    }
+}
+
 // fp32 [B, 8, 8, 8, c] -> TF 'SAME' average pool (window K, mean over the valid cells) -> act(scale * . + shift) -> triplet.
 // One CTA = one sample x 32 channels: the 512 x 32 tile is staged once in shared memory (64 KB) and the box sum is done
 // separably in place (three passes of 64 lines of 8 voxels, one warp per line, lane = channel).
@@ -287,6 +319,12 @@ int mups_pool3d_bf16x3(const void* x_bf16_dev, int64_t B, int D, int c_total, in
     MUPS_REQUIRE(is_max ? k == 2 : (k >= 1 && k <= 5), "mups_pool3d_bf16x3: window %d", k);
     const int Do = is_max ? D / 2 : D;
     const long long n = (long long)B * Do * Do * Do * (w / 8);
+    if (is_max && (long long)B * D * D * D * (c_total / 8) < 0xFFFFFFFFll) {
+        maxpool2_x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            static_cast<const __nv_bfloat16*>(x_bf16_dev), (unsigned)n, D, c_total, c_off, w, static_cast<__nv_bfloat16*>(y_bf16_dev), y_total, y_off);
+        MUPS_CHECK_LAUNCH();
+        return MUPS_OK;
+    }
     const int grid = (int)((n + 255) / 256 < 32 * kNumSMs ? (n + 255) / 256 : 32 * kNumSMs);
     pool3_x3_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16_dev), B, D, c_total, c_off, w, k,
                                                                            is_max, static_cast<__nv_bfloat16*>(y_bf16_dev), y_total, y_off);
