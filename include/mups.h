@@ -207,6 +207,13 @@ int mups_avgpool3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int c_total
  * channel axis accumulates a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32 (writing its y_f32_dev output).  The two entry points
  * below turn fp32 back into triplets; they replace nothing in the reference (which computes in fp32 throughout,
  * models/experts_n_est.py:155-314) -- they are what lets the bf16 tensor cores reproduce it to ~1e-5 relative. */
+/* mups_conv3d_bn_relu with its output written as triplets straight from the epilogue (no fp32 round trip): output channels
+ * [0, split) form the triplet [hi | lo | hi] of part width `split` at channels [cout_off, cout_off + 3 split) of y_bf16_dev, channels
+ * [split, cout) a second triplet of part width cout - split right behind it (split == cout: one triplet; split a multiple of 16).
+ * Bit-identical to the fp32 output followed by mups_split_bf16x3. */
+int mups_conv3d_bn_relu_x3(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
+                           int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
+                           int cout_total, int cout_off, int split, mups_stream stream);
 /* fp32 src_dev [rows, src_stride], columns [src_off, src_off + w_src) -> triplet at channels [dst_off, dst_off + 3 w_dst) of
  * dst_bf16_dev [rows, dst_stride] (w_dst >= w_src, a multiple of 8; channels [w_src, w_dst) of every part are zero). */
 int mups_split_bf16x3(const float* src_dev, int64_t rows, int src_stride, int src_off, int w_src, void* dst_bf16_dev, int dst_stride,

@@ -32,7 +32,7 @@ EXPORTS = (
     "mups_gmm_create", "mups_gmm_size", "mups_gmm_is_separable", "mups_gmm_destroy",
     "mups_3dmfv", "mups_features", "mups_ball_query_select", "mups_3dmfv_selected",
     "mups_moe_pack_input", "mups_conv3d_bn_relu", "mups_pool3d", "mups_conv1_split_bn_relu", "mups_avgpool3d_bn_relu",
-    "mups_split_bf16x3", "mups_pool3d_bf16x3", "mups_avgpool3d_f32_bn_relu_x3",
+    "mups_split_bf16x3", "mups_pool3d_bf16x3", "mups_avgpool3d_f32_bn_relu_x3", "mups_conv3d_bn_relu_x3",
 )
 
 _lib = None
@@ -99,6 +99,8 @@ def load():
     L.mups_pool3d_bf16x3.restype = i32
     L.mups_avgpool3d_f32_bn_relu_x3.argtypes = [vp, i64, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]
     L.mups_avgpool3d_f32_bn_relu_x3.restype = i32
+    L.mups_conv3d_bn_relu_x3.argtypes = [vp, i64, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, i32, vp]
+    L.mups_conv3d_bn_relu_x3.restype = i32
     if L.mups_abi_version() != 1:
         raise RuntimeError("libmups_b200.so ABI version %d, expected 1" % L.mups_abi_version())
     _lib = L

@@ -59,6 +59,10 @@ struct ConvArgs {
     __nv_bfloat16* y2;
     long long y2_stride;
     int y2_off, split, relu_upto;
+    // bf16x3 output (moe_split.cu): x3_split > 0 -> every value leaves as hi = bf16(v), lo = bf16(v - hi); output channels
+    // [0, x3_split) form the triplet [hi | lo | hi] of part width x3_split at cout_off, channels [x3_split, Cout) a second triplet
+    // of part width Cout - x3_split right behind it
+    int x3_split;
     int n_tiles, m_ctas, n_fast;     // channel tiles per voxel tile, voxel-tile CTAs; the grid is 1-D: with n_fast the channel tile is
 };                                   // the FAST index, so that the CTAs that read the same activation tile run together (L2 hits)
 
@@ -120,8 +124,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 
+// bf16x3 output: channel co of this launch -> (first channel of its triplet's hi part relative to cout_off, part width)
+__device__ __forceinline__ void x3_dest(const ConvArgs& a, int co, int& ych, int& w) {
+    if (co < a.x3_split) { ych = co; w = a.x3_split; }
+    else { ych = 3 * a.x3_split + (co - a.x3_split); w = a.Cout - a.x3_split; }
+}
+__device__ __forceinline__ uint32_t pack_lo2(float f0, float f1, uint32_t hi_packed) {
+    const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi_packed));
+    float r0 = f0 - h.x, r1 = f1 - h.y;                   // exact in fp32
+    if (!(fabsf(r0) <= 3.0e38f)) r0 = 0.f;                // inf / NaN: the high part carries it alone (as moe_split.cu::split8)
+    if (!(fabsf(r1) <= 3.0e38f)) r1 = 0.f;
+    const __nv_bfloat162 p = __floats2bfloat162_rn(r0, r1);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+
 // Epilogue of both convolution kernels: the four epilogue warps read their 32 TMEM lanes x 16 columns at a time, apply
 // scale / shift (+ ReLU), pack to bf16 and store into the channel slice of the NDHWC output (and / or the fp32 output).
+template <bool X3>      // X3: bf16x3 (triplet) output; its own instantiation, so that the plain kernels' code is untouched by it
 __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_acc, uint32_t tmem_base, int warp, int lane, int n0, int tile0,
                                               const int (&tb0)[2], const int (&tz0)[2]) {
     // warp w may touch TMEM lanes [32 (w % 4), +32)
@@ -180,9 +199,23 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_ac
                     p = __floats2bfloat162_rn(f[10], f[11]); hi.y = *reinterpret_cast<uint32_t*>(&p);
                     p = __floats2bfloat162_rn(f[12], f[13]); hi.z = *reinterpret_cast<uint32_t*>(&p);
                     p = __floats2bfloat162_rn(f[14], f[15]); hi.w = *reinterpret_cast<uint32_t*>(&p);
+                    if (X3) {                   // triplet output: n0 + cc is a multiple of 16, as is x3_split -- one triplet per group
+                        int ych, w3;
+                        x3_dest(a, n0 + cc, ych, w3);
+                        __nv_bfloat16* d3 = a.y + voxel * a.y_stride + a.cout_off + ych;
+                        uint4 l0, l1;
+                        l0.x = pack_lo2(f[0], f[1], lo.x);   l0.y = pack_lo2(f[2], f[3], lo.y);
+                        l0.z = pack_lo2(f[4], f[5], lo.z);   l0.w = pack_lo2(f[6], f[7], lo.w);
+                        l1.x = pack_lo2(f[8], f[9], hi.x);   l1.y = pack_lo2(f[10], f[11], hi.y);
+                        l1.z = pack_lo2(f[12], f[13], hi.z); l1.w = pack_lo2(f[14], f[15], hi.w);
+                        reinterpret_cast<uint4*>(d3)[0] = lo;            reinterpret_cast<uint4*>(d3)[1] = hi;
+                        reinterpret_cast<uint4*>(d3 + w3)[0] = l0;       reinterpret_cast<uint4*>(d3 + w3)[1] = l1;
+                        reinterpret_cast<uint4*>(d3 + 2 * w3)[0] = lo;   reinterpret_cast<uint4*>(d3 + 2 * w3)[1] = hi;
+                    } else {
                     uint4* dst = reinterpret_cast<uint4*>(yrow + cc);
                     dst[0] = lo;
                     dst[1] = hi;
+                    }
                 }
                 if (frow) {
 #pragma unroll
@@ -196,6 +229,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvArgs& a, uint32_t bar_ac
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 
+template <bool X3>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -284,7 +318,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             if (++s == a.stages) { s = 0; ph ^= 1; }
         }
     } else {
-        conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
+        conv_epilogue<X3>(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
     }
     __syncthreads();
     if (warp == 2) {
@@ -392,7 +426,7 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
             if (++s == a.stages) { s = 0; ph ^= 1; }
         }
     } else {
-        conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
+        conv_epilogue<false>(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
     }
     __syncthreads();
     cluster_sync_all();                 // nobody leaves while the peer may still write into this CTA's shared memory / barriers
@@ -415,6 +449,7 @@ struct HaloArgs { int na, nb, a_box_bytes, swap, ext, nz, pair; };   // A stages
 
 // Epilogue of the z-halo kernel with SWAPPED operand roles (accumulator = [128 output channels (TMEM lanes)] x [256 voxels
 // (columns)]): a thread owns one output channel, a warp's store covers 32 consecutive channels of one voxel (64 bytes).
+template <bool X3>
 __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_t bar_acc, uint32_t tmem_base, int warp, int lane, int n0,
                                                       long long voxel0, int voxels, bool live) {
     mbar_wait(bar_acc, 0);
@@ -424,7 +459,9 @@ __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_
     const bool real = co < a.Cout;
     const float sc = real ? __ldg(a.scale + co) : 0.f, sh = real ? __ldg(a.shift + co) : 0.f;
     // live == false: the all-out-of-bounds partner of an odd batch's last CTA pair -- it waits for its MMAs, stores nothing
-    __nv_bfloat16* ycol = (a.y && live) ? a.y + voxel0 * a.y_stride + a.cout_off + co : nullptr;
+    int ych = co, w3 = 0;
+    if (X3) x3_dest(a, co < a.Cout ? co : a.Cout - 1, ych, w3);
+    __nv_bfloat16* ycol = (a.y && live && (real || !X3)) ? a.y + voxel0 * a.y_stride + a.cout_off + ych : nullptr;
     float* fcol = (a.y_f32 && live) ? a.y_f32 + voxel0 * (long long)a.Cout + co : nullptr;
     for (int j0 = 0; j0 < (live ? voxels : 0); j0 += 64) {           // voxels is 256 or 512: four TMEM loads in flight per wait
         uint32_t v[4][16];
@@ -437,7 +474,17 @@ __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_
             for (int j = 0; j < 16; ++j) {
                 float t = fmaf(__uint_as_float(v[h][j]), sc, sh);
                 t = a.relu ? fmaxf(t, 0.f) : t;
-                if (ycol) ycol[(long long)(j0 + 16 * h + j) * a.y_stride] = __float2bfloat16_rn(t);
+                if (ycol) {
+                    const __nv_bfloat16 hb = __float2bfloat16_rn(t);
+                    __nv_bfloat16* d = ycol + (long long)(j0 + 16 * h + j) * a.y_stride;
+                    d[0] = hb;
+                    if (X3) {
+                        float r = t - __bfloat162float(hb);
+                        if (!(fabsf(r) <= 3.0e38f)) r = 0.f;
+                        d[w3] = __float2bfloat16_rn(r);
+                        d[2 * w3] = hb;
+                    }
+                }
                 if (fcol && real) fcol[(long long)(j0 + 16 * h + j) * a.Cout] = t;
             }
         }
@@ -445,6 +492,7 @@ __device__ __forceinline__ void conv_epilogue_swapped(const ConvArgs& a, uint32_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 
+template <bool X3>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_half,
                     const ConvArgs a, const HaloArgs h) {
@@ -570,9 +618,9 @@ conv3d_zhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             if (++sa == h.na) { sa = 0; pa ^= 1; }
         }
     } else if (h.swap) {
-        conv_epilogue_swapped(a, bar_acc, tmem_base, warp, lane, n0, (long long)tb0[0] * 512 + tz0[0] * 64, h.nz * 64, sample < a.B);
+        conv_epilogue_swapped<X3>(a, bar_acc, tmem_base, warp, lane, n0, (long long)tb0[0] * 512 + tz0[0] * 64, h.nz * 64, sample < a.B);
     } else {
-        conv_epilogue(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
+        conv_epilogue<X3>(a, bar_acc, tmem_base, warp, lane, n0, tile0, tb0, tz0);
     }
     __syncthreads();
     if (h.pair) cluster_sync_all();     // nobody leaves while the peer may still write into this CTA's shared memory / barriers
@@ -854,7 +902,7 @@ int mups_avgpool3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int c_total
                        PoolEpi{scale_dev, shift_dev, relu, y_total, y_off}, stream);
 }
 
-struct ConvSplit { void* y2; int y2_total, y2_off, split, relu_upto; };
+struct ConvSplit { void* y2; int y2_total, y2_off, split, relu_upto; int x3_split; };   // y2 == nullptr, x3_split > 0: bf16x3 output
 
 static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
                        int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
@@ -867,6 +915,16 @@ int mups_conv3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total,
                        cout_total, cout_off, y_f32_dev, nullptr, stream);
 }
 
+int mups_conv3d_bn_relu_x3(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
+                           int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
+                           int cout_total, int cout_off, int split, mups_stream stream) {
+    MUPS_REQUIRE(y_bf16_dev, "mups_conv3d_bn_relu_x3: NULL output");
+    MUPS_REQUIRE(split >= 16, "mups_conv3d_bn_relu_x3: split %d of %d output channels (multiples of 16)", split, cout);
+    const ConvSplit sp{nullptr, 0, 0, 0, 0, split};
+    return conv_launch(x_bf16_dev, B, D, cin_total, cin_off, cin, w_bf16_dev, cin_w, cout, k, scale_dev, shift_dev, relu, y_bf16_dev,
+                       cout_total, cout_off, nullptr, &sp, stream);
+}
+
 int mups_conv1_split_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
                              int cin_w, int cout, const float* scale_dev, const float* shift_dev, int relu_upto, void* y1_bf16_dev,
                              int y1_total, int y1_off, int split, void* y2_bf16_dev, int y2_total, int y2_off, mups_stream stream) {
@@ -875,14 +933,16 @@ int mups_conv1_split_bn_relu(const void* x_bf16_dev, int64_t B, int D, int cin_t
     MUPS_REQUIRE(y2_total % 8 == 0 && y2_off % 8 == 0 && y2_off + (cout - split) <= y2_total && y1_off + split <= y1_total,
                  "mups_conv1_split_bn_relu: output channel slices");
     MUPS_REQUIRE(relu_upto >= 0 && relu_upto <= cout, "mups_conv1_split_bn_relu: relu_upto %d", relu_upto);
-    const ConvSplit sp{y2_bf16_dev, y2_total, y2_off, split, relu_upto};
+    const ConvSplit sp{y2_bf16_dev, y2_total, y2_off, split, relu_upto, 0};
     return conv_launch(x_bf16_dev, B, D, cin_total, cin_off, cin, w_bf16_dev, cin_w, cout, 1, scale_dev, shift_dev, relu_upto > 0, y1_bf16_dev,
                        y1_total, y1_off, nullptr, &sp, stream);
 }
 
 static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, int cin_off, int cin, const void* w_bf16_dev,
                        int cin_w, int cout, int k, const float* scale_dev, const float* shift_dev, int relu, void* y_bf16_dev,
-                       int cout_total, int cout_off, float* y_f32_dev, const ConvSplit* sp, mups_stream stream) {
+                       int cout_total, int cout_off, float* y_f32_dev, const ConvSplit* sp_in, mups_stream stream) {
+    const int x3_split = (sp_in && !sp_in->y2) ? sp_in->x3_split : 0;
+    const ConvSplit* sp = (sp_in && sp_in->y2) ? sp_in : nullptr;
     MUPS_REQUIRE(x_bf16_dev && w_bf16_dev && scale_dev && shift_dev && (y_bf16_dev || y_f32_dev), "mups_conv3d_bn_relu: NULL buffer");
     MUPS_REQUIRE(B >= 1 && B < (1ll << 30), "mups_conv3d_bn_relu: B=%lld out of range", (long long)B);
     MUPS_REQUIRE(D == 1 || D == 2 || D == 4 || D == 8, "mups_conv3d_bn_relu: volume edge %d (1, 2, 4 or 8)", D);
@@ -891,8 +951,10 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
                  "mups_conv3d_bn_relu: input channels (%d of %d at %d) must be multiples of 8", cin, cin_total, cin_off);
     MUPS_REQUIRE(cin_w >= cin && cin_w % 8 == 0, "mups_conv3d_bn_relu: weight inner dimension %d", cin_w);
     MUPS_REQUIRE(cout >= 16 && cout % 16 == 0, "mups_conv3d_bn_relu: output channels %d must be a multiple of 16", cout);
-    MUPS_REQUIRE(!y_bf16_dev || (cout_total % 8 == 0 && cout_off % 8 == 0 && cout_off + (sp ? sp->split : cout) <= cout_total),
-                 "mups_conv3d_bn_relu: output channel slice (%d of %d at %d)", cout, cout_total, cout_off);
+    MUPS_REQUIRE(!y_bf16_dev || (cout_total % 8 == 0 && cout_off % 8 == 0 && cout_off + (x3_split ? 3 * cout : sp ? sp->split : cout) <= cout_total),
+                 "mups_conv3d_bn_relu: output channel slice (%d of %d at %d)", x3_split ? 3 * cout : cout, cout_total, cout_off);
+    MUPS_REQUIRE(!x3_split || (y_bf16_dev && x3_split >= 16 && x3_split % 16 == 0 && x3_split <= cout),
+                 "mups_conv3d_bn_relu_x3: split %d of %d output channels (multiples of 16)", x3_split, cout);
     MUPS_REQUIRE(((reinterpret_cast<uintptr_t>(scale_dev) | reinterpret_cast<uintptr_t>(shift_dev)) & 15) == 0,
                  "mups_conv3d_bn_relu: scale / shift must be 16-byte aligned");
     EncodeTiledFn enc = encode_tiled();
@@ -915,6 +977,7 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     a.y2 = sp ? static_cast<__nv_bfloat16*>(sp->y2) : nullptr;
     a.y2_stride = sp ? sp->y2_total : 0; a.y2_off = sp ? sp->y2_off : 0; a.split = sp ? sp->split : cout;
     a.relu_upto = sp ? sp->relu_upto : cout;
+    a.x3_split = x3_split;
     const int vox = D * D * D;
     a.dz_box = vox >= kTileM ? kTileM / (D * D) : D;
     a.b_box = vox >= kTileM ? 1 : kTileM / vox;
@@ -1011,14 +1074,15 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
         if (r != CUDA_SUCCESS) { set_error("mups_conv3d_bn_relu: weight tensor map rejected (CUresult %d)", (int)r); return MUPS_ERR_CUDA; }
     }
     if (zhalo) {
-        MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_zhalo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const auto zkernel = x3_split ? conv3d_zhalo_kernel<true> : conv3d_zhalo_kernel<false>;
+        MUPS_CUDA_TRY(cudaFuncSetAttribute(zkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         unsigned gx = (unsigned)(h.nz == 8 ? m_tiles / 4 : m_tiles / 2);
         // conv_variant 9: CTA pairs (clusters of two CTAs: two samples, or the two halves of one) that share every weight tile -- each
         // CTA fetches half of its rows and the TMA unit multicasts them into both shared memories: a fifth to a quarter less L2 -> SM
         // traffic per CTA (the weights are 3 x 16 of 112 KB per activation box at k = 3, 5 x 16 of 144 KB at k = 5)
         h.pair = (g_conv_variant.load() == 9 && gx >= 2 * kNumSMs) ? 1 : 0;
         if (!h.pair) {
-            conv3d_zhalo_kernel<<<dim3(gx, (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, map_w, a, h);
+            zkernel<<<dim3(gx, (unsigned)(cout / n_tile)), kConvThreads, smem, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, map_w, a, h);
             MUPS_CHECK_LAUNCH();
             return MUPS_OK;
         }
@@ -1043,14 +1107,15 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        MUPS_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3d_zhalo_kernel, map_x, map_w, map_wh, a, h));
+        MUPS_CUDA_TRY(cudaLaunchKernelEx(&cfg, zkernel, map_x, map_w, map_wh, a, h));
         MUPS_CHECK_LAUNCH();
         return MUPS_OK;
     }
-    MUPS_CUDA_TRY(cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const auto tkernel = x3_split ? conv3d_tcgen05_kernel<true> : conv3d_tcgen05_kernel<false>;
+    MUPS_CUDA_TRY(cudaFuncSetAttribute(tkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     a.n_tiles = cout / n_tile;
     a.m_ctas = (int)((m_tiles + a.m_sub - 1) / a.m_sub);
-    if (k == 1 && a.m_sub == 1 && n_tile >= 32 && n_tile % 32 == 0 && m_tiles >= 4 * kNumSMs && g_conv_variant.load() == 8) {
+    if (k == 1 && a.m_sub == 1 && n_tile >= 32 && n_tile % 32 == 0 && m_tiles >= 4 * kNumSMs && g_conv_variant.load() == 8 && !x3_split) {
         // CTA pairs sharing the weight tile by TMA multicast (see conv3d_pair_kernel)
         CUtensorMap map_wh;
         const cuuint64_t dims[3] = {(cuuint64_t)cin_w, (cuuint64_t)cout, (cuuint64_t)(k * k * k)};
@@ -1078,7 +1143,7 @@ static int conv_launch(const void* x_bf16_dev, int64_t B, int D, int cin_total, 
     }
     a.n_fast = getenv("MUPS_CONV_NSLOW") ? 0 : 1;            // benchmarking override: channel tile as the slow index
     MUPS_REQUIRE(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles <= 0x7FFFFFFFll, "mups_conv3d_bn_relu: grid too large");
-    conv3d_tcgen05_kernel<<<(unsigned)(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles), kConvThreads, smem,
+    tkernel<<<(unsigned)(((m_tiles + a.m_sub - 1) / a.m_sub) * a.n_tiles), kConvThreads, smem,
                             static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
     MUPS_CHECK_LAUNCH();
     return MUPS_OK;

@@ -142,6 +142,20 @@ def conv3d_f32(x, cin_off, cin, layer):
     return out
 
 
+def conv3d_x3(x, cin_off, cin, layer, out, cout_off, split=None):
+    """The convolution with its output written as triplets by the epilogue (mups_conv3d_bn_relu_x3): output channels [0, split)
+    -> the triplet of part width ``split`` at channels [cout_off, ...) of ``out``, channels [split, cout_pad) -> a second triplet
+    right behind it (default: one triplet of part width cout_pad).  cin_off, cin, cout_off: PHYSICAL channels."""
+    B = int(x.shape[0])
+    D = int(x.shape[1]) if x.ndim == 5 else 1
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mups_conv3d_bn_relu_x3(
+            _ptr(x), B, D, int(x.shape[-1]), int(cin_off), int(cin), _ptr(layer.w), layer.cin_pad, layer.cout_pad, layer.k, _ptr(layer.scale),
+            _ptr(layer.shift), 1 if layer.relu else 0, _ptr(out), int(out.shape[-1]), int(cout_off),
+            int(layer.cout_pad if split is None else split), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)),
+            "mups_conv3d_bn_relu_x3")
+
+
 def split_x3(src, src_off, w_src, dst, dst_off, w_dst):
     """fp32 src [rows, n] columns [src_off, src_off + w_src) -> the triplet [hi | lo | hi] at channels [dst_off, dst_off + 3 w_dst)
     of the bf16 tensor dst [..., Ct] (mups_split_bf16x3)."""
@@ -267,7 +281,7 @@ class _PackedInception(object):
 
 class _PackedInceptionX3(object):
     """The inception module in bf16x3 mode: the module's output holds the triplets of its four branches
-    [one | a | b | pool] one after the other; every convolution leaves through its fp32 output and split_x3."""
+    [one | a | b | pool] one after the other, written by the convolutions' own epilogues (conv3d_x3)."""
 
     def __init__(self, m, device, in_map, cin_pad, in_segs):
         self.k0, self.in_segs = m.k0, list(in_segs)
@@ -295,16 +309,14 @@ class _PackedInceptionX3(object):
         """x: triplet tensor; cin_off, cin: LOGICAL channels (whole segments)."""
         out = torch.empty(tuple(x.shape[:-1]) + (3 * self.c_out,), dtype=torch.bfloat16, device=x.device)
         nf, ap, bp = self.nf, self.a.cout_pad, self.b.cout_pad
-        split_x3(conv3d_f32(x, 3 * cin_off, 3 * cin, self.one), 0, nf, out, 0, nf)
-        if self.ab is not None:
-            t = conv3d_f32(out, 0, 3 * nf, self.ab)
-            split_x3(t, 0, ap, out, 3 * nf, ap)
-            split_x3(t, ap, bp, out, 3 * (nf + ap), bp)
+        conv3d_x3(x, 3 * cin_off, 3 * cin, self.one, out, 0)
+        if self.ab is not None:                  # output channels [a | b] -> the two triplets [a | b] of the module's output
+            conv3d_x3(out, 0, 3 * nf, self.ab, out, 3 * nf, ap)
         else:
-            split_x3(conv3d_f32(out, 0, 3 * nf, self.a), 0, ap, out, 3 * nf, ap)
-            split_x3(conv3d_f32(out, 0, 3 * nf, self.b), 0, bp, out, 3 * (nf + ap), bp)
+            conv3d_x3(out, 0, 3 * nf, self.a, out, 3 * nf)
+            conv3d_x3(out, 0, 3 * nf, self.b, out, 3 * (nf + ap))
         if self.k0 == 1:                         # a 1-wide average pool is the identity
-            split_x3(conv3d_f32(x, 3 * cin_off, 3 * cin, self.pool), 0, nf, out, 3 * (nf + ap + bp), nf)
+            conv3d_x3(x, 3 * cin_off, 3 * cin, self.pool, out, 3 * (nf + ap + bp))
         else:
             t = conv3d_f32(x, 3 * cin_off, 3 * cin, self.pool_raw)
             avgpool_f32_x3(t, x.shape[0], x.shape[1], nf, self.k0, self.pool.scale, self.pool.shift, True, out, 3 * (nf + ap + bp))
@@ -384,9 +396,9 @@ class TensorCoreExperts(object):
     def _run_fc(self, layers, x):
         for l in layers[:-1]:
             if self.x3:
-                t = conv3d_f32(x, 0, int(x.shape[-1]), l)
-                x = torch.empty((x.shape[0], 3 * l.cout_pad), dtype=torch.bfloat16, device=x.device)
-                split_x3(t, 0, l.cout_pad, x, 0, l.cout_pad)
+                y = torch.empty((x.shape[0], 3 * l.cout_pad), dtype=torch.bfloat16, device=x.device)
+                conv3d_x3(x, 0, int(x.shape[-1]), l, y, 0)
+                x = y
             else:
                 x = conv3d_bn_relu(x, 0, int(x.shape[-1]), l)
         last = layers[-1]

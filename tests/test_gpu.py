@@ -982,6 +982,24 @@ def test_tcgen05_conv3d_against_torch(D, k, ct, cin_off, cin, cout, B):
     got = out.reshape(-1, cout + 16)
     assert torch.all(got[:, :8] == 7.0) and torch.all(got[:, 8 + cout:] == 7.0), "wrote outside its channel slice"
     assert torch.equal(got[:, 8:8 + cout], f32.to(torch.bfloat16)), "bf16 output is not the rounded fp32 output"
+    # bf16x3 output straight from the epilogue (mups_conv3d_bn_relu_x3): one triplet, and two triplets split at 16 / at cout - 16 --
+    # bit-identical to splitting the fp32 output (hi = bf16(v), lo = bf16(v - hi))
+    hi = f32.to(torch.bfloat16)
+    lo = (f32 - hi.float()).to(torch.bfloat16)
+    for split in sorted({cout, 16, max(16, cout - 16)}):
+        out3 = torch.full(shape[:-1] + (3 * cout + 16,), 7.0, dtype=torch.bfloat16, device=dev)
+        me.conv3d_x3(x, cin_off, cin, layer, out3, 8, split)
+        torch.cuda.synchronize()
+        g3 = out3.reshape(-1, 3 * cout + 16)
+        assert torch.all(g3[:, :8] == 7.0) and torch.all(g3[:, 8 + 3 * cout:] == 7.0), "wrote outside its triplets"
+        off = 8
+        for c0, c1 in ((0, split), (split, cout)):
+            w3 = c1 - c0
+            if w3 == 0:
+                continue
+            assert torch.equal(g3[:, off:off + w3], hi[:, c0:c1]) and torch.equal(g3[:, off + 2 * w3:off + 3 * w3], hi[:, c0:c1])
+            assert torch.equal(g3[:, off + w3:off + 2 * w3], lo[:, c0:c1])
+            off += 3 * w3
     if k == 1 and B >= 149:
         # >= 592 voxel tiles: conv_variant 8 = CTA pairs that share every weight tile through TMA multicast (odd tile counts get an
         # all-out-of-bounds partner): same MMAs in the same order

@@ -75,6 +75,9 @@ def test_argument_validation_without_compute():
     assert b"triplet" in L.mups_last_error()
     assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 0, 32, 3, 1, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # max pool: window 2 only
     assert L.mups_pool3d_bf16x3(one, 4, 8, 96, 8, 32, 3, 0, one, 96, 0, None) == _lib.MUPS_ERR_INVALID   # triplet [8, 104) of 96
+    assert L.mups_conv3d_bn_relu_x3(one, 4, 8, 64, 0, 64, one, 64, 64, 3, one, one, 1, one, 192, 0, 24, None) == _lib.MUPS_ERR_INVALID
+    assert b"split" in L.mups_last_error()
+    assert L.mups_conv3d_bn_relu_x3(one, 4, 8, 64, 0, 64, one, 64, 64, 3, one, one, 1, one, 128, 0, 64, None) == _lib.MUPS_ERR_INVALID  # 192 channels needed
     assert L.mups_avgpool3d_f32_bn_relu_x3(one, 4, 8, 64, 1, one, one, 1, one, 192, 0, None) == _lib.MUPS_ERR_INVALID  # window >= 2
     assert L.mups_avgpool3d_f32_bn_relu_x3(one, 4, 8, 64, 3, one, one, 1, one, 192, 8, None) == _lib.MUPS_ERR_INVALID  # triplet [8, 200) of 192
     for name, top in ((b"pool_variant", 1), (b"conv_variant", 9)):
@@ -392,7 +395,7 @@ def test_bf16x3_engine_logic_on_emulated_ops(monkeypatch):
     from nesti_net_b200.experts_net import ExpertsNormalEstimator, angular_rms_deg, avg_pool_same
 
     def emu_conv(x, cin_off, cin, layer, out=None, cout_off=0, out_f32=None):
-        assert out is None and out_f32 is not None, "the bf16x3 mode only uses the convolution's fp32 output"
+        assert out is None and out_f32 is not None, "in bf16x3 mode the plain entry point is only used for its fp32 output"
         assert x.dtype == torch.bfloat16 and cin % 8 == 0 and cin_off % 8 == 0 and cin <= layer.cin_pad
         xs = x.float()[..., cin_off:cin_off + cin]
         if xs.ndim == 2:
@@ -429,6 +432,16 @@ def test_bf16x3_engine_logic_on_emulated_ops(monkeypatch):
         p = avg_pool_same(src.view(B, D, D, D, c).permute(0, 4, 1, 2, 3), k).permute(0, 2, 3, 4, 1).reshape(-1, c) * scale + shift
         put_triplet(out.view(-1, out.shape[-1]), y_off, c, torch.relu(p) if relu else p)
 
+    def emu_conv_x3(x, cin_off, cin, layer, out, cout_off, split=None):
+        split = layer.cout_pad if split is None else split
+        assert split % 16 == 0 and 16 <= split <= layer.cout_pad and cout_off % 8 == 0 and cout_off + 3 * layer.cout_pad <= out.shape[-1]
+        f = emu_conv(x, cin_off, cin, layer, None, 0, torch.empty((x.numel() // x.shape[-1], layer.cout_pad)))
+        o2 = out.view(-1, out.shape[-1])
+        put_triplet(o2, cout_off, split, f[:, :split])
+        if split < layer.cout_pad:
+            put_triplet(o2, cout_off + 3 * split, layer.cout_pad - split, f[:, split:])
+
+    monkeypatch.setattr(me, "conv3d_x3", emu_conv_x3)
     monkeypatch.setattr(me, "avgpool_f32_x3", emu_avgpool_f32)
     monkeypatch.setattr(me, "conv3d_bn_relu", emu_conv)
     monkeypatch.setattr(me, "split_x3", emu_split)
