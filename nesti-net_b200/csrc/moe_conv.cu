@@ -21,6 +21,9 @@
 //                           block) serves all k dz-taps; 128-channel tiles with the operand roles swapped (weights = M,
 //                           voxels = N = 256), out-of-volume slices left out of the MMAs, whole sample per CTA for large batches
 //   avgpool8_tile_kernel, maxpool2_kernel, pool3d_kernel, pack_mups_bf16_kernel: the pools and the input conversion
+//   conv3d_pair_kernel      (conv_variant 8) / the pair mode of the z-halo kernel (conv_variant 9): CTA pairs that share every weight
+//                           tile through TMA multicast -- bit-identical, measured, not faster: kept as tested variants
+// The <true> instantiations of the two kernels write bf16x3 triplets (hi, lo pairs; moe_split.cu) instead of plain bf16.
 // Every mbarrier wait is bounded: a barrier that never completes traps instead of hanging the GPU.
 #include <cstdlib>
 

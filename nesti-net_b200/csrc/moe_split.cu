@@ -8,8 +8,9 @@
 //     activations   [ hi | lo | hi ]            (a "triplet": 3 w channels for w logical ones)
 //     weights       [ w_hi | w_hi | w_lo ]      (expanded once on the host, moe_engine.PackedConv)
 //
-// so mups_conv3d_bn_relu (moe_conv.cu: TMA, tcgen05.mma, TMEM) runs unchanged on 3 x the K extent and writes its fp32
-// output (scale / shift / ReLU applied) to a scratch tensor; the two kernels here turn fp32 back into triplets:
+// so the convolution kernels of moe_conv.cu (TMA, tcgen05.mma, TMEM) run with an unchanged main loop on 3 x the K extent; their
+// epilogue writes the next layer's triplets itself (mups_conv3d_bn_relu_x3: the X3 instantiation of the kernels).  The kernels
+// here are the rest of the mode:
 //
 //   split3_kernel      fp32 [rows, src_stride] columns [src_off, +w_src) -> triplet at channels [dst_off, +3 w_dst) of
 //                      an NDHWC bf16 tensor (w_src <= w_dst: the tail is zero padding, e.g. MuPS' 20 channels per scale
