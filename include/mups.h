@@ -203,10 +203,11 @@ int mups_avgpool3d_bn_relu(const void* x_bf16_dev, int64_t B, int D, int c_total
 
 /* ---- bf16x3 ("split") mode of the consumer: fp32-grade results from the same tensor-core kernels ------------------------
  * A value is carried as hi = bf16(v), lo = bf16(v - hi); a tensor of w logical channels is stored as the TRIPLET
- * [hi | lo | hi] (3 w channels), the weights are expanded to [w_hi | w_hi | w_lo], and mups_conv3d_bn_relu over the 3 x longer
- * channel axis accumulates a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32 (writing its y_f32_dev output).  The two entry points
- * below turn fp32 back into triplets; they replace nothing in the reference (which computes in fp32 throughout,
- * models/experts_n_est.py:155-314) -- they are what lets the bf16 tensor cores reproduce it to ~1e-5 relative. */
+ * [hi | lo | hi] (3 w channels), the weights are expanded to [w_hi | w_hi | w_lo], and the convolution over the 3 x longer
+ * channel axis accumulates a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32.  The entry points below are that convolution with
+ * triplets out, the conversion of an fp32 tensor (the MuPS input) into triplets, and the pools between triplets; they replace
+ * nothing in the reference (which computes in fp32 throughout, models/experts_n_est.py:155-314) -- they are what lets the
+ * bf16 tensor cores reproduce it to ~1e-5 relative (normals within 0.001 degrees). */
 /* mups_conv3d_bn_relu with its output written as triplets straight from the epilogue (no fp32 round trip): output channels
  * [0, split) form the triplet [hi | lo | hi] of part width `split` at channels [cout_off, cout_off + 3 split) of y_bf16_dev, channels
  * [split, cout) a second triplet of part width cout - split right behind it (split == cout: one triplet; split a multiple of 16).
